@@ -1,0 +1,334 @@
+// scalar_ops.cuh -- the 1-CTA "scalar kernel": everything between two streaming passes.
+//
+// It (1) sums the per-CTA partials of the pass that just ended in a fixed order (thread t
+// adds partials t, t+256, ... then a fixed shuffle/shared-memory tree: deterministic, no
+// atomics), or takes the rank-ordered sum of the all-gathered packets on multi-GPU runs, and
+// (2) lets one thread do the scalar work the reference does on the host between cuBLAS calls
+// (par/L-BFGS.cu:219-272) or inside its line-search loops: rho/alpha/beta of the two-loop
+// recursion, gamma, the descent safeguard, the line-search state machine, the curvature gate
+// and ring-buffer bookkeeping, the convergence test.  All of it stays in HBM (DevState); the
+// host reads nothing back except the 16-byte Ctrl block in host-stepped mode.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+#include "state.h"
+
+namespace lb {
+
+constexpr int kScalarThreads = 256;
+
+// which boundary values a packet carries besides the sums
+enum PackKind : int { PACK_NONE = 0, PACK_X0 = 1, PACK_DIR = 2, PACK_ACCEPT = 3 };
+// packet layout (doubles): [0..4] sums, [5] x_first, [6] x_last, [7] g_first, [8] g_last,
+// [9] d_first, [10] d_last, [11] spare
+
+__device__ __forceinline__ void reduce_partials(const double *__restrict__ partials, int grid, int nq,
+                                                double *out /* shared, >= nq */)
+{
+    __shared__ double sm[kScalarThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = 0; q < nq; ++q) {
+        double v = 0.0;
+        for (int i = threadIdx.x; i < grid; i += kScalarThreads)
+            v += partials[(size_t)q * grid + i];
+        v = warp_sum(v);
+        if (lane == 0) sm[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            double w = (lane < kScalarThreads / 32) ? sm[lane] : 0.0;
+#pragma unroll
+            for (int o = kScalarThreads / 64; o > 0; o >>= 1)
+                w += __shfl_xor_sync(0xffffffffu, w, o);
+            if (lane == 0) out[q] = w;
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ int nq_of(int op)
+{
+    switch (op) {
+    case OP_INIT:
+    case OP_ACCEPT: return 5;
+    case OP_LS_STEP: return 3;
+    case OP_SG:
+    case OP_L1:
+    case OP_L2:
+    case OP_COMPACT_DIR: return 1;
+    default: return 0;
+    }
+}
+
+// multi-GPU: local sums + boundary values -> st->send (the host then all-gathers kPacket
+// doubles per rank into st->recv)
+__global__ void __launch_bounds__(kScalarThreads) k_pack(DevState *st, int op, int kind, int nparts)
+{
+    __shared__ double r[kMaxQ];
+    reduce_partials(st->partials, nparts, nq_of(op), r);
+    if (threadIdx.x != 0) return;
+    double *s = st->send;
+    for (int q = 0; q < 5; ++q) s[q] = (q < nq_of(op)) ? r[q] : 0.0;
+    const long long n = st->n;
+    for (int q = 5; q < kPacket; ++q) s[q] = 0.0;
+    if (n > 0) {
+        if (kind == PACK_X0) {
+            s[5] = st->x[0];
+            s[6] = st->x[n - 1];
+        } else if (kind == PACK_ACCEPT) {
+            s[5] = st->x_alt[0]; // the accept kernel wrote the new iterate to x_alt
+            s[6] = st->x_alt[n - 1];
+            s[7] = st->g[0];
+            s[8] = st->g[n - 1];
+        } else if (kind == PACK_DIR) {
+            s[9] = st->w[0];
+            s[10] = st->w[n - 1];
+        }
+    }
+}
+
+__device__ __forceinline__ void write_trace(DevState *st)
+{
+    if (st->trace && st->k < st->trace_rows) {
+        double *row = st->trace + (size_t)st->k * LBFGSB200_TRACE_COLS;
+        row[0] = (double)st->k;
+        row[1] = st->f;
+        row[2] = sqrt(st->gg);
+        row[3] = st->ls.alpha;
+        row[4] = (double)st->ls.trials;
+        row[5] = (double)st->h;
+        row[6] = st->n > 0 ? st->x[0] : 0.0;
+        row[7] = st->n > 0 ? st->x[st->n / 2] : 0.0;
+    }
+}
+
+// Commit the candidate pair sitting in the spare slot (seq/lbfgs.cpp:182-190: pop the oldest
+// when full, push the new pair).
+__device__ __forceinline__ void commit_pair(DevState *st, double sy, double yy, double sg)
+{
+    const int sp = spare_slot(*st);
+    st->rho[sp] = 1.0 / sy; // seq/lbfgs.cpp:102 (computed once here, not twice per iteration)
+    st->sy[sp] = sy;
+    st->yy[sp] = yy;
+    st->skip[sp] = 0;
+    if (st->h < st->m)
+        st->h += 1;
+    else
+        st->base = (st->base + 1) % st->nslots;
+    st->sg = sg;
+    st->sg_valid = 1;
+}
+
+__device__ void scalar_logic(DevState *st, int op, int p, const double *r)
+{
+    const bool seq = st->profile == LBFGSB200_PROFILE_SEQ;
+    switch (op) {
+    case OP_INIT: {
+        // x0 evaluation (seq/lbfgs.cpp:28-30): the accept kernel ran with alpha=0 on d=0
+        double *t = st->x; st->x = st->x_alt; st->x_alt = t;
+        st->f = r[0];
+        st->gg = r[1];
+        st->k = 0;
+        st->h = 0;
+        st->base = 0;
+        st->sg_valid = 0;
+        st->need_sg = 0;
+        st->steepest = 0;
+        st->status = LBFGSB200_RUNNING;
+        st->trial_evals = 0;
+        st->vec_streams = 0.0;
+        st->ctrl.ls_active = 0;
+        st->ctrl.done = 0;
+        st->ctrl.h = 0;
+        st->ctrl.k = 0;
+        st->ls.alpha = 0.0;
+        st->ls.trials = 0;
+        break;
+    }
+    case OP_ITER_BEGIN: {
+        if (st->ctrl.done) return;
+        if (seq && sqrt(st->gg) < st->tolerance) { // seq/lbfgs.cpp:80-84
+            st->status = LBFGSB200_CONVERGED;
+            st->ctrl.done = 1;
+            return;
+        }
+        if (st->k >= st->max_iterations) {
+            st->status = LBFGSB200_MAX_ITER;
+            st->ctrl.done = 1;
+            return;
+        }
+        st->need_sg = 0;
+        const int h = st->h;
+        int steepest = (st->k == 0 || h == 0); // seq/lbfgs.cpp:87
+        if (!steepest) {
+            const int newest = slot_of(*st, h - 1);
+            if (seq) {
+                for (int i = 0; i < h; ++i)
+                    if (!isfinite(st->rho[slot_of(*st, i)])) steepest = 1; // :103-108
+                const double gamma = st->sy[newest] / st->yy[newest];      // :117
+                if (gamma <= 0 || !isfinite(gamma)) steepest = 1;          // :119-124
+                st->gamma = gamma;
+            } else {
+                // par/L-BFGS.cu:241-255
+                const double ys = st->sy[newest], yy = st->yy[newest];
+                st->gamma = (yy > 0 && ys > 1e-10) ? ys / yy : 1.0;
+            }
+            if (!steepest) {
+                if (st->sg_valid) {
+                    const double a = st->skip[newest] ? 0.0 : st->rho[newest] * st->sg; // :109
+                    st->alpha[h - 1] = a;
+                    st->coef = a;
+                } else {
+                    st->need_sg = 1;
+                }
+            }
+        }
+        st->steepest = steepest;
+        // bytes model: two-loop = 8h-1 vector streams, d=-g = 2
+        st->vec_streams += steepest ? 2.0 : (8.0 * h - 1.0) + (st->need_sg ? 2.0 : 0.0);
+        break;
+    }
+    case OP_SG: {
+        if (st->ctrl.done || !st->need_sg) return;
+        const int newest = slot_of(*st, st->h - 1);
+        st->sg = r[0];
+        const double a = st->skip[newest] ? 0.0 : st->rho[newest] * st->sg;
+        st->alpha[st->h - 1] = a;
+        st->coef = a;
+        st->need_sg = 0;
+        break;
+    }
+    case OP_L1: {
+        const int h = st->h;
+        if (st->ctrl.done || st->steepest || p >= h) return;
+        if (p > 0) {
+            const int sl = slot_of(*st, p - 1);
+            const double a = st->skip[sl] ? 0.0 : st->rho[sl] * r[0]; // alpha_i = rho_i (s_i . q)
+            st->alpha[p - 1] = a;
+            st->coef = a;
+        } else {
+            const int sl = slot_of(*st, 0);
+            const double beta = st->rho[sl] * r[0]; // seq/lbfgs.cpp:136, r = gamma q
+            st->coef = st->skip[sl] ? 0.0 : st->alpha[0] - beta;
+        }
+        break;
+    }
+    case OP_L2: {
+        const int h = st->h;
+        if (st->ctrl.done || st->steepest || p >= h) return;
+        if (p < h - 1) {
+            const int sl = slot_of(*st, p + 1);
+            const double beta = st->rho[sl] * r[0];
+            st->coef = st->skip[sl] ? 0.0 : st->alpha[p + 1] - beta; // seq/lbfgs.cpp:139
+        } else {
+            st->gd = r[0]; // seq/lbfgs.cpp:146
+            if (seq && st->gd >= 0) { // :147-153, resolved by k_steepest + OP_LS_INIT
+                st->steepest = 1;
+                st->vec_streams += 2.0;
+            }
+        }
+        break;
+    }
+    case OP_LS_INIT: {
+        if (st->ctrl.done) return;
+        if (st->steepest) {
+            // d = -g  =>  g.d = -(g.g) with the same summation order (negation is exact)
+            st->gd = -st->gg;
+            st->dL = -st->gL;
+            st->dR = -st->gR;
+        }
+        ls_begin(st->lsp, st->ls, st->f, st->gd);
+        st->ctrl.ls_active = 1;
+        break;
+    }
+    case OP_LS_STEP: {
+        if (st->ctrl.done || !st->ctrl.ls_active) return;
+        st->trial_evals += 1;
+        st->vec_streams += 2.0; // trial: reads x, d
+        const int cont = ls_step(st->lsp, st->ls, r[0], r[1]);
+        if (!cont) {
+            st->ctrl.ls_active = 0;
+            if (st->ls.alpha < 1e-10) { // seq/lbfgs.cpp:164-168: give up, keep the OLD x
+                st->status = LBFGSB200_LS_FAILED;
+                st->ctrl.done = 1;
+            }
+        }
+        break;
+    }
+    case OP_ACCEPT: {
+        if (st->ctrl.done) return;
+        double *t = st->x; st->x = st->x_alt; st->x_alt = t; // x <- x_new
+        st->f = r[0];
+        st->gg = r[1];
+        const double sy = r[2], yy = r[3], sg = r[4];
+        if (seq) {
+            if (sy > 0) commit_pair(st, sy, yy, sg); // seq/lbfgs.cpp:181-190
+            else st->sg_valid = 0;                   // :192-195 "Skipping update"
+        } else {
+            commit_pair(st, sy, yy, sg);             // par/L-BFGS.cu:332-333: always overwritten
+            if (sy <= 1e-10) {                       // par/L-BFGS.cu:222-223
+                const int newest = slot_of(*st, st->h - 1);
+                st->skip[newest] = 1;
+                st->rho[newest] = 0.0;
+            }
+        }
+        st->vec_streams += 7.0; // accept: reads x, d, g ; writes x, g, s, y
+        write_trace(st);
+        st->k += 1;
+        if (!seq && sqrt(st->gg) <= st->tolerance) { // par/L-BFGS.cu:353-357
+            st->status = LBFGSB200_CONVERGED;
+            st->ctrl.done = 1;
+        } else if (st->k >= st->max_iterations) {    // seq/lbfgs.cpp:201
+            st->status = LBFGSB200_MAX_ITER;
+            st->ctrl.done = 1;
+        }
+        st->ctrl.h = st->h;
+        st->ctrl.k = st->k;
+        break;
+    }
+    default: break;
+    }
+}
+
+// from_comm = 0: single GPU, sums come straight from the partials of the last pass.
+// from_comm = 1: sums are the rank-ordered totals of the all-gathered packets (identical
+//                bits on every rank); neighbours' boundary values are picked up as halo.
+__global__ void __launch_bounds__(kScalarThreads)
+k_scalar(DevState *st, int op, int p, int from_comm, int pack_kind, int nparts)
+{
+    __shared__ double r[kMaxQ];
+    const int nq = nq_of(op);
+    if (!from_comm) {
+        reduce_partials(st->partials, nparts, nq, r);
+    } else if (threadIdx.x == 0) {
+        const double *rv = st->recv;
+        for (int q = 0; q < nq; ++q) {
+            double v = 0.0;
+            for (int k = 0; k < st->nranks; ++k) v += rv[k * kPacket + q];
+            r[q] = v;
+        }
+        const int left = st->rank - 1, right = st->rank + 1;
+        if (pack_kind == PACK_X0 || pack_kind == PACK_ACCEPT) {
+            st->xL = left >= 0 ? rv[left * kPacket + 6] : 0.0;
+            st->xR = right < st->nranks ? rv[right * kPacket + 5] : 0.0;
+            st->gL = left >= 0 ? rv[left * kPacket + 8] : 0.0;
+            st->gR = right < st->nranks ? rv[right * kPacket + 7] : 0.0;
+        } else if (pack_kind == PACK_DIR) {
+            st->dL = left >= 0 ? rv[left * kPacket + 10] : 0.0;
+            st->dR = right < st->nranks ? rv[right * kPacket + 9] : 0.0;
+        }
+    }
+    if (threadIdx.x == 0) scalar_logic(st, op, p, r);
+}
+
+// unit-test surface: finalise nq partial sums into d_out[0..nq)
+__global__ void __launch_bounds__(kScalarThreads)
+k_finalize(const double *partials, int grid, int nq, double *d_out, int take_sqrt)
+{
+    __shared__ double r[kMaxQ];
+    reduce_partials(partials, grid, nq, r);
+    if (threadIdx.x == 0)
+        for (int q = 0; q < nq; ++q) d_out[q] = take_sqrt ? sqrt(r[q]) : r[q];
+}
+
+} // namespace lb

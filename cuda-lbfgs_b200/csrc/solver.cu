@@ -1,0 +1,837 @@
+// solver.cu -- host side of the B200-native L-BFGS hot path and its C ABI (include/lbfgsb200.h).
+//
+// The host does no arithmetic on problem data.  It owns the HBM arena, launches the streaming
+// kernels (kernels.cuh) and the 1-CTA scalar kernel (scalar_ops.cuh) in the fixed order of one
+// L-BFGS iteration, and -- in host-stepped mode -- reads back a 16-byte control block once per
+// line-search trial to learn whether the device-side state machine wants another trial.  In
+// graph mode (graph.cuh) even that disappears: the iteration loop and the trial loop are CUDA
+// graph WHILE nodes whose conditions the scalar kernel sets on the device.
+//
+// Replaces: LBFGS() seq/lbfgs.cpp:17-203 ; LBFGS_CUDA() par/L-BFGS.cu:105-382 and the four
+// inlined-line-search variants.  There is no CPU fallback: without a CUDA device every compute
+// entry point returns LBFGSB200_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/lbfgsb200.h"
+#include "comm.h"
+#include "kernels.cuh"
+#include "scalar_ops.cuh"
+#include "state.h"
+
+namespace lb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            lb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,                  \
+                          cudaGetErrorString(e_));                                            \
+            return LBFGSB200_ERR_CUDA;                                                        \
+        }                                                                                     \
+    } while (0)
+
+#define LB_TRY(expr)                                                                          \
+    do {                                                                                      \
+        int rc_ = (expr);                                                                     \
+        if (rc_ < 0) return rc_;                                                              \
+    } while (0)
+
+static int sm_count(int *out)
+{
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    *out = sms;
+    return 0;
+}
+
+// streaming-kernel grid: a multiple of the SM count (kCtasPerSm resident CTAs per SM), shrunk
+// for tiny problems so idle CTAs do not pad the partial arrays
+static int pick_grid(long long n, int sms, int forced, int ctas_per_sm = kCtasPerSm)
+{
+    if (forced > 0) return forced;
+    const long long nvec = n >> 1;
+    long long tiles = (nvec + kTileVec - 1) / kTileVec;
+    if (tiles < 1) tiles = 1;
+    const long long full = (long long)sms * ctas_per_sm;
+    return (int)(tiles < full ? tiles : full);
+}
+
+enum KClass { KC_PASS = 0, KC_TRIAL = 1, KC_ACCEPT = 2, KC_OTHER = 3 };
+
+} // namespace lb
+
+using namespace lb;
+
+struct lbfgsb200_solver {
+    int sms = 0;
+    int objective = 0;
+    size_t n_global = 0, n_local = 0, offset = 0, stride = 0;
+    int nslots = 0;
+    int grid = 1, grid_accept = 1;
+    lbfgsb200_params_t params;
+    lbfgsb200_comm *comm = nullptr;
+
+    double *arena = nullptr;    // x, x_alt, g, w, S[nslots], Y[nslots]
+    double *partials = nullptr; // [kMaxQ][grid]
+    double *pkt = nullptr;      // send [kPacket] + recv [nranks][kPacket]
+    double *trace = nullptr;
+    size_t trace_rows = 0;
+    DevState *d_st = nullptr;
+    Ctrl *h_ctrl = nullptr;     // pinned
+    DevState h_snapshot;        // last state copied back
+
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    bool x0_set = false;
+    int64_t k_host = 0; // accepts launched so far: an upper bound on the device's h
+    int64_t launches = 0;
+    double last_ms = 0.0;
+    double streams_at_start = 0.0; // vec_streams when the last timed region began
+    double streams_last = 0.0;
+
+    // per-class event pairs (iterate_profiled)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_ev[4];
+};
+
+namespace lb {
+
+struct ClassTimer {
+    lbfgsb200_solver *s;
+    int cls;
+    ClassTimer(lbfgsb200_solver *s_, int cls_) : s(s_), cls(cls_)
+    {
+        if (s->profiling) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, s->stream);
+            s->prof_ev[cls].push_back(e);
+        }
+    }
+    ~ClassTimer()
+    {
+        if (s->profiling) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, s->stream);
+            s->prof_ev[cls].push_back(e);
+        }
+    }
+};
+
+// scalar step: on one GPU the scalar kernel sums the partials itself; on several the local sums
+// and halo values are packed, all-gathered (one small NCCL call) and summed in rank order.
+static int scalar_step(lbfgsb200_solver *s, int op, int p, int pack_kind)
+{
+    const int nparts = (op == OP_ACCEPT || op == OP_INIT) ? s->grid_accept : s->grid;
+    const bool needs_data = (op != OP_ITER_BEGIN && op != OP_LS_INIT);
+    if (s->comm && s->comm->nranks > 1 && needs_data) {
+        k_pack<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, op, pack_kind, nparts);
+        LB_TRY(comm_allgather(s->comm, s->pkt, s->pkt + kPacket, kPacket, s->stream));
+        k_scalar<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, op, p, 1, pack_kind, nparts);
+        s->launches += 2;
+    } else {
+        k_scalar<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, op, p, 0, PACK_NONE, nparts);
+        s->launches += 1;
+    }
+    return 0;
+}
+
+// search direction: seq/lbfgs.cpp:86-153
+static int launch_direction(lbfgsb200_solver *s)
+{
+    const int m = s->params.m;
+    const int h_upper = (int)(s->k_host < m ? s->k_host : m);
+    LB_TRY(scalar_step(s, OP_ITER_BEGIN, 0, PACK_NONE));
+    if (h_upper > 0) {
+        {
+            ClassTimer t(s, KC_OTHER);
+            k_dot_sg<<<s->grid, kThreads, 0, s->stream>>>(s->d_st);
+            s->launches += 1;
+        }
+        LB_TRY(scalar_step(s, OP_SG, 0, PACK_NONE));
+        for (int p = h_upper - 1; p >= 0; --p) {
+            {
+                ClassTimer t(s, KC_PASS);
+                k_two_loop_pass<<<s->grid, kThreads, 0, s->stream>>>(s->d_st, 1, p);
+                s->launches += 1;
+            }
+            LB_TRY(scalar_step(s, OP_L1, p, PACK_NONE));
+        }
+        for (int p = 0; p < h_upper; ++p) {
+            {
+                ClassTimer t(s, KC_PASS);
+                k_two_loop_pass<<<s->grid, kThreads, 0, s->stream>>>(s->d_st, 2, p);
+                s->launches += 1;
+            }
+            LB_TRY(scalar_step(s, OP_L2, p, PACK_DIR));
+        }
+    }
+    {
+        ClassTimer t(s, KC_OTHER);
+        k_steepest<<<s->grid, kThreads, 0, s->stream>>>(s->d_st);
+        s->launches += 1;
+    }
+    LB_TRY(scalar_step(s, OP_LS_INIT, 0, PACK_NONE));
+    return 0;
+}
+
+static int read_ctrl(lbfgsb200_solver *s)
+{
+    CUDA_TRY(cudaMemcpyAsync(s->h_ctrl, &s->d_st->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost,
+                             s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+static int snapshot(lbfgsb200_solver *s)
+{
+    CUDA_TRY(cudaMemcpyAsync(&s->h_snapshot, s->d_st, sizeof(DevState), cudaMemcpyDeviceToHost,
+                             s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// host-stepped iteration loop
+static int run_stepped(lbfgsb200_solver *s, int64_t iterations)
+{
+    for (int64_t it = 0; it < iterations; ++it) {
+        LB_TRY(launch_direction(s));
+        // line search: one fused evaluation + one device-side decision per trial
+        do {
+            {
+                ClassTimer t(s, KC_TRIAL);
+                k_trial<<<s->grid, kThreads, 0, s->stream>>>(s->d_st);
+                s->launches += 1;
+            }
+            LB_TRY(scalar_step(s, OP_LS_STEP, 0, PACK_NONE));
+            LB_TRY(read_ctrl(s));
+        } while (s->h_ctrl->ls_active && !s->h_ctrl->done);
+        if (s->h_ctrl->done) break;
+        {
+            ClassTimer t(s, KC_ACCEPT);
+            k_accept<<<s->grid_accept, kThreads, 0, s->stream>>>(s->d_st, 0);
+            s->launches += 1;
+        }
+        LB_TRY(scalar_step(s, OP_ACCEPT, 0, PACK_ACCEPT));
+        s->k_host += 1;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static int do_iterate(lbfgsb200_solver *s, int64_t iterations)
+{
+    if (!s->x0_set) {
+        set_error("iterate: set_x0 has not been called");
+        return LBFGSB200_ERR_INVALID;
+    }
+    s->streams_at_start = s->h_snapshot.vec_streams;
+    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    int rc = run_stepped(s, iterations);
+    CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+    if (rc < 0) return rc;
+    LB_TRY(snapshot(s));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->last_ms = ms;
+    s->streams_last = s->h_snapshot.vec_streams - s->streams_at_start;
+    return s->h_snapshot.status;
+}
+
+} // namespace lb
+
+// ====================================================================
+// C ABI
+// ====================================================================
+extern "C" {
+
+int lbfgsb200_version(void) { return LBFGSB200_VERSION; }
+
+const char *lbfgsb200_last_error(void) { return lb::g_err; }
+
+const char *lbfgsb200_strerror(int status)
+{
+    switch (status) {
+    case LBFGSB200_CONVERGED: return "converged";
+    case LBFGSB200_MAX_ITER: return "maximum iterations reached";
+    case LBFGSB200_LS_FAILED: return "line search failed";
+    case LBFGSB200_RUNNING: return "running";
+    case LBFGSB200_ERR_INVALID: return "invalid argument";
+    case LBFGSB200_ERR_CUDA: return "CUDA error";
+    case LBFGSB200_ERR_NCCL: return "NCCL error";
+    case LBFGSB200_ERR_NOMEM: return "out of device memory";
+    default: return "unknown status";
+    }
+}
+
+int lbfgsb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int lbfgsb200_params_default(lbfgsb200_params_t *p, int flavor)
+{
+    if (!p) return LBFGSB200_ERR_INVALID;
+    memset(p, 0, sizeof *p);
+    p->m = 10;                 // seq/lbfgs.h:23
+    p->max_iterations = 1000;  // seq/lbfgs.h:22
+    p->tolerance = 1e-5;       // seq/lbfgs.h:24
+    p->line_search = LBFGSB200_LS_BACKTRACKING;
+    p->flavor = flavor;
+    p->profile = LBFGSB200_PROFILE_SEQ;
+    p->direction = LBFGSB200_DIR_TWO_LOOP;
+    p->c1 = 1e-4;                                         // seq/config.h:5, par/constants.h:5
+    p->c2 = (flavor == LBFGSB200_FLAVOR_PAR) ? 0.7 : 0.9; // par/constants.h:6 / seq/config.h:6
+    p->step0 = 1.0;                                       // INITIAL_STEP_SIZE
+    p->shrink = 0.5;                                      // BACKTRACKING_ALPHA
+    p->backtracking_tol = 1e-8;                           // BACKTRACKING_TOL
+    p->wolfe_min = 1e-10;                                 // WOLFE_INTERP_MIN
+    p->ls_max_trials = 20;
+    p->use_graph = 0;
+    p->verbose = 0;
+    p->grid_ctas = 0;
+    return 0;
+}
+
+void lbfgsb200_shard_range(size_t n_global, int rank, int nranks, size_t *offset, size_t *n_local)
+{
+    // even-sized shards so every shard starts on a 16-byte boundary of the global vector and
+    // the double2 path never straddles ranks; the last rank takes the remainder
+    if (nranks < 1) nranks = 1;
+    size_t chunk = (n_global / (size_t)nranks) & ~(size_t)1;
+    size_t off = chunk * (size_t)rank;
+    size_t len = (rank == nranks - 1) ? n_global - off : chunk;
+    if (offset) *offset = off;
+    if (n_local) *n_local = len;
+}
+
+static int check_params(const lbfgsb200_params_t *p)
+{
+    if (!p) { set_error("params is NULL"); return LBFGSB200_ERR_INVALID; }
+    if (p->m < 1 || p->m > LBFGSB200_MAX_M) { set_error("m=%d out of range 1..%d", p->m, LBFGSB200_MAX_M); return LBFGSB200_ERR_INVALID; }
+    if (p->line_search < 0 || p->line_search > 3) {
+        // the reference throws std::invalid_argument("Unknown line search method") seq/lbfgs.cpp:69
+        set_error("Unknown line search method: %d", p->line_search);
+        return LBFGSB200_ERR_INVALID;
+    }
+    if (p->flavor < 0 || p->flavor > 1 || p->profile < 0 || p->profile > 1 || p->direction < 0 ||
+        p->direction > 1) {
+        set_error("bad flavor/profile/direction");
+        return LBFGSB200_ERR_INVALID;
+    }
+    if (p->max_iterations < 0 || p->ls_max_trials < 1) { set_error("bad iteration limits"); return LBFGSB200_ERR_INVALID; }
+    return 0;
+}
+
+int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
+                     const lbfgsb200_params_t *params, lbfgsb200_comm_t *comm, size_t trace_rows)
+{
+    if (!out) return LBFGSB200_ERR_INVALID;
+    *out = nullptr;
+    LB_TRY(check_params(params));
+    if (objective < 0 || objective > LBFGSB200_OBJ_TRIDIAG) { set_error("unknown objective %d", objective); return LBFGSB200_ERR_INVALID; }
+    if (n_global == 0) { set_error("n must be > 0"); return LBFGSB200_ERR_INVALID; }
+    if (lbfgsb200_device_count() < 1) {
+        set_error("no usable CUDA device: this library has no CPU fallback");
+        return LBFGSB200_ERR_CUDA;
+    }
+    lbfgsb200_solver *s = new (std::nothrow) lbfgsb200_solver;
+    if (!s) return LBFGSB200_ERR_NOMEM;
+    s->params = *params;
+    s->objective = objective;
+    s->comm = comm;
+    s->n_global = n_global;
+    const int rank = comm ? comm->rank : 0, nranks = comm ? comm->nranks : 1;
+    if (nranks > kMaxRanks) { set_error("at most %d ranks", kMaxRanks); delete s; return LBFGSB200_ERR_INVALID; }
+    lbfgsb200_shard_range(n_global, rank, nranks, &s->offset, &s->n_local);
+    if (s->n_local == 0) { set_error("rank %d owns no elements (n=%zu, ranks=%d)", rank, n_global, nranks); delete s; return LBFGSB200_ERR_INVALID; }
+    s->nslots = params->m + 1;
+    s->stride = (s->n_local + 31) / 32 * 32; // 256-byte rows
+    int rc = sm_count(&s->sms);
+    if (rc < 0) { delete s; return rc; }
+    s->grid = pick_grid((long long)s->n_local, s->sms, params->grid_ctas);
+    s->grid_accept = pick_grid((long long)s->n_local, s->sms, params->grid_ctas, kCtasPerSmAccept);
+
+    const size_t nvecs = 4 + 2 * (size_t)s->nslots;
+    const size_t arena_bytes = nvecs * s->stride * sizeof(double);
+    cudaError_t e = cudaMalloc(&s->arena, arena_bytes);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc of %.2f GB for %zu vectors failed: %s", arena_bytes / 1e9, nvecs, cudaGetErrorString(e));
+        cudaGetLastError();
+        delete s;
+        return LBFGSB200_ERR_NOMEM;
+    }
+#define CREATE_TRY(expr)                                                                      \
+    do {                                                                                      \
+        cudaError_t e2_ = (expr);                                                             \
+        if (e2_ != cudaSuccess) {                                                             \
+            set_error("%s failed: %s", #expr, cudaGetErrorString(e2_));                       \
+            lbfgsb200_destroy(s);                                                             \
+            return LBFGSB200_ERR_CUDA;                                                        \
+        }                                                                                     \
+    } while (0)
+    CREATE_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreate(&s->ev0));
+    CREATE_TRY(cudaEventCreate(&s->ev1));
+    CREATE_TRY(cudaMemsetAsync(s->arena, 0, arena_bytes, s->stream));
+    CREATE_TRY(cudaMalloc(&s->partials, sizeof(double) * kMaxQ * (size_t)s->grid));
+    CREATE_TRY(cudaMemsetAsync(s->partials, 0, sizeof(double) * kMaxQ * (size_t)s->grid, s->stream));
+    CREATE_TRY(cudaMalloc(&s->pkt, sizeof(double) * kPacket * (size_t)(nranks + 1)));
+    CREATE_TRY(cudaMemsetAsync(s->pkt, 0, sizeof(double) * kPacket * (size_t)(nranks + 1), s->stream));
+    s->trace_rows = trace_rows;
+    if (trace_rows) {
+        CREATE_TRY(cudaMalloc(&s->trace, sizeof(double) * LBFGSB200_TRACE_COLS * trace_rows));
+        CREATE_TRY(cudaMemsetAsync(s->trace, 0, sizeof(double) * LBFGSB200_TRACE_COLS * trace_rows, s->stream));
+    }
+    CREATE_TRY(cudaMalloc(&s->d_st, sizeof(DevState)));
+    CREATE_TRY(cudaHostAlloc(&s->h_ctrl, sizeof(Ctrl), cudaHostAllocDefault));
+    memset(s->h_ctrl, 0, sizeof(Ctrl));
+
+    DevState &st = s->h_snapshot;
+    memset(&st, 0, sizeof st);
+    st.n = (long long)s->n_local;
+    st.goff = (long long)s->offset;
+    st.nglob = (long long)n_global;
+    st.m = params->m;
+    st.nslots = s->nslots;
+    st.objective = objective;
+    st.profile = params->profile;
+    st.direction = params->direction;
+    st.max_iterations = params->max_iterations;
+    st.tolerance = params->tolerance;
+    st.rank = rank;
+    st.nranks = nranks;
+    st.grid = s->grid;
+    st.grid_accept = s->grid_accept;
+    st.x = s->arena;
+    st.x_alt = s->arena + s->stride;
+    st.g = s->arena + 2 * s->stride;
+    st.w = s->arena + 3 * s->stride;
+    st.S = s->arena + 4 * s->stride;
+    st.Y = st.S + (size_t)s->nslots * s->stride;
+    st.stride = (long long)s->stride;
+    st.partials = s->partials;
+    st.send = s->pkt;
+    st.recv = s->pkt + kPacket;
+    st.trace = s->trace;
+    st.trace_rows = (long long)trace_rows;
+    st.lsp.kind = params->line_search;
+    st.lsp.flavor = params->flavor;
+    st.lsp.max_trials = params->ls_max_trials;
+    st.lsp.c1 = params->c1;
+    st.lsp.c2 = params->c2;
+    st.lsp.step0 = params->step0;
+    st.lsp.shrink = params->shrink;
+    st.lsp.bt_tol = params->backtracking_tol;
+    st.lsp.wolfe_min = params->wolfe_min;
+    st.status = LBFGSB200_RUNNING;
+    CREATE_TRY(cudaMemcpyAsync(s->d_st, &st, sizeof st, cudaMemcpyHostToDevice, s->stream));
+    CREATE_TRY(cudaStreamSynchronize(s->stream));
+#undef CREATE_TRY
+    *out = s;
+    return 0;
+}
+
+void lbfgsb200_destroy(lbfgsb200_solver_t *s)
+{
+    if (!s) return;
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (int c = 0; c < 4; ++c)
+        for (cudaEvent_t e : s->prof_ev[c]) cudaEventDestroy(e);
+    if (s->arena) cudaFree(s->arena);
+    if (s->partials) cudaFree(s->partials);
+    if (s->pkt) cudaFree(s->pkt);
+    if (s->trace) cudaFree(s->trace);
+    if (s->d_st) cudaFree(s->d_st);
+    if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+size_t lbfgsb200_local_size(const lbfgsb200_solver_t *s) { return s ? s->n_local : 0; }
+
+int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local)
+{
+    if (!s || !x0_local) { set_error("set_x0: NULL argument"); return LBFGSB200_ERR_INVALID; }
+    // restore the pristine state (ring empty, pointers un-swapped), then evaluate f(x0), g(x0)
+    DevState st = s->h_snapshot;
+    st.x = s->arena;
+    st.x_alt = s->arena + s->stride;
+    st.base = 0;
+    st.h = 0;
+    st.k = 0;
+    st.ctrl.ls_active = 0;
+    st.ctrl.done = 0;
+    st.ctrl.h = 0;
+    st.ctrl.k = 0;
+    st.status = LBFGSB200_RUNNING;
+    st.xL = st.xR = st.dL = st.dR = st.gL = st.gR = 0.0;
+    CUDA_TRY(cudaMemcpyAsync(s->d_st, &st, sizeof st, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream)); // st is a stack object
+    CUDA_TRY(cudaMemcpyAsync(st.x, x0_local, s->n_local * sizeof(double), cudaMemcpyDefault, s->stream));
+    CUDA_TRY(cudaMemsetAsync(st.w, 0, s->stride * sizeof(double), s->stream)); // d = 0
+    if (s->comm && s->comm->nranks > 1) {
+        // neighbours' boundary x before the first evaluation (one-element halo)
+        k_pack<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, -1, PACK_X0, 0);
+        LB_TRY(comm_allgather(s->comm, s->pkt, s->pkt + kPacket, kPacket, s->stream));
+        k_scalar<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, -1, 0, 1, PACK_X0, 0);
+        s->launches += 2;
+    }
+    k_accept<<<s->grid_accept, kThreads, 0, s->stream>>>(s->d_st, 1);
+    s->launches += 1;
+    LB_TRY(scalar_step(s, OP_INIT, 0, PACK_ACCEPT));
+    CUDA_TRY(cudaGetLastError());
+    LB_TRY(snapshot(s));
+    s->k_host = 0;
+    s->x0_set = true;
+    return 0;
+}
+
+int lbfgsb200_iterate(lbfgsb200_solver_t *s, int64_t iterations)
+{
+    if (!s) return LBFGSB200_ERR_INVALID;
+    s->profiling = false;
+    return do_iterate(s, iterations);
+}
+
+int lbfgsb200_iterate_profiled(lbfgsb200_solver_t *s, int64_t iterations, double class_ms[4],
+                               int64_t class_launches[4])
+{
+    if (!s) return LBFGSB200_ERR_INVALID;
+    for (int c = 0; c < 4; ++c) {
+        for (cudaEvent_t e : s->prof_ev[c]) cudaEventDestroy(e);
+        s->prof_ev[c].clear();
+    }
+    s->profiling = true;
+    int rc = do_iterate(s, iterations);
+    s->profiling = false;
+    if (rc < 0) return rc;
+    for (int c = 0; c < 4; ++c) {
+        double total = 0.0;
+        const std::vector<cudaEvent_t> &v = s->prof_ev[c];
+        for (size_t i = 0; i + 1 < v.size(); i += 2) {
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, v[i], v[i + 1]));
+            total += ms;
+        }
+        if (class_ms) class_ms[c] = total;
+        if (class_launches) class_launches[c] = (int64_t)(v.size() / 2);
+    }
+    return rc;
+}
+
+int lbfgsb200_get_x(lbfgsb200_solver_t *s, double *x_local_out)
+{
+    if (!s || !x_local_out) return LBFGSB200_ERR_INVALID;
+    CUDA_TRY(cudaMemcpyAsync(x_local_out, s->h_snapshot.x, s->n_local * sizeof(double), cudaMemcpyDefault, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+int lbfgsb200_get_result(lbfgsb200_solver_t *s, lbfgsb200_result_t *r)
+{
+    if (!s || !r) return LBFGSB200_ERR_INVALID;
+    const DevState &st = s->h_snapshot;
+    r->status = st.status;
+    r->iterations = st.k;
+    r->trial_evals = st.trial_evals;
+    r->kernel_launches = s->launches;
+    r->f = st.f;
+    r->gnorm = sqrt(st.gg);
+    r->device_ms = s->last_ms;
+    r->bytes_moved = s->streams_last * 8.0 * (double)s->n_local;
+    return 0;
+}
+
+int64_t lbfgsb200_get_trace(lbfgsb200_solver_t *s, double *rows, size_t max_rows)
+{
+    if (!s || !rows || !s->trace) return 0;
+    size_t have = (size_t)s->h_snapshot.k;
+    if (have > s->trace_rows) have = s->trace_rows;
+    if (have > max_rows) have = max_rows;
+    if (have == 0) return 0;
+    if (cudaMemcpy(rows, s->trace, have * LBFGSB200_TRACE_COLS * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return LBFGSB200_ERR_CUDA;
+    return (int64_t)have;
+}
+
+int lbfgsb200_solve(int objective, size_t n, const double *x0_host, double *x_out_host,
+                    const lbfgsb200_params_t *params, lbfgsb200_result_t *result, double *trace,
+                    size_t trace_rows)
+{
+    if (!x0_host || !x_out_host || !params) { set_error("solve: NULL argument"); return LBFGSB200_ERR_INVALID; }
+    lbfgsb200_solver *s = nullptr;
+    int rc = lbfgsb200_create(&s, objective, n, params, nullptr, trace ? trace_rows : 0);
+    if (rc < 0) return rc;
+    rc = lbfgsb200_set_x0(s, x0_host);
+    if (rc >= 0) rc = lbfgsb200_iterate(s, (int64_t)params->max_iterations + 1);
+    if (rc >= 0) {
+        int rc2 = lbfgsb200_get_x(s, x_out_host);
+        if (rc2 < 0) rc = rc2;
+    }
+    if (rc >= 0 && result) lbfgsb200_get_result(s, result);
+    if (rc >= 0 && trace) lbfgsb200_get_trace(s, trace, trace_rows);
+    if (rc >= 0 && params->verbose) {
+        // the reference's per-iteration line (seq/lbfgs.cpp:77-78), printed from the device trace
+        std::vector<double> rows((size_t)LBFGSB200_TRACE_COLS * (trace_rows ? trace_rows : 1));
+        int64_t got = trace ? lbfgsb200_get_trace(s, rows.data(), trace_rows) : 0;
+        for (int64_t i = 0; i < got; ++i)
+            printf("Iteration %lld, f = %g, |grad| = %g\n", (long long)rows[i * LBFGSB200_TRACE_COLS] + 1,
+                   rows[i * LBFGSB200_TRACE_COLS + 1], rows[i * LBFGSB200_TRACE_COLS + 2]);
+    }
+    lbfgsb200_destroy(s);
+    return rc;
+}
+
+// --------------------------------------------------------------------
+// unit-test surface
+// --------------------------------------------------------------------
+struct Scratch {
+    double *p = nullptr;
+    cudaStream_t st;
+    int grid = 1;
+    int init(long long n, cudaStream_t stream, size_t extra_doubles = 0, int ctas_per_sm = kCtasPerSm)
+    {
+        st = stream;
+        int sms = 0;
+        LB_TRY(sm_count(&sms));
+        grid = pick_grid(n, sms, 0, ctas_per_sm);
+        CUDA_TRY(cudaMallocAsync(&p, sizeof(double) * (kMaxQ * (size_t)grid + extra_doubles), st));
+        return 0;
+    }
+    double *extra() { return p + kMaxQ * (size_t)grid; }
+    ~Scratch() { if (p) cudaFreeAsync(p, st); }
+};
+
+int lbfgsb200_dot(const double *a, const double *b, size_t n, double *d_out, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch sc;
+    LB_TRY(sc.init((long long)n, st));
+    k_dot<<<sc.grid, kThreads, 0, st>>>(a, b, (long long)n, sc.p);
+    k_finalize<<<1, kScalarThreads, 0, st>>>(sc.p, sc.grid, 1, d_out, 0);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int lbfgsb200_nrm2(const double *a, size_t n, double *d_out, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch sc;
+    LB_TRY(sc.init((long long)n, st));
+    k_dot<<<sc.grid, kThreads, 0, st>>>(a, a, (long long)n, sc.p);
+    k_finalize<<<1, kScalarThreads, 0, st>>>(sc.p, sc.grid, 1, d_out, 1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int lbfgsb200_axpy(const double *d_alpha, const double *x, double *y, size_t n, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    int sms = 0;
+    LB_TRY(sm_count(&sms));
+    k_axpy<true><<<pick_grid((long long)n, sms, 0), kThreads, 0, st>>>(d_alpha, x, y, y, (long long)n);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int lbfgsb200_scal(const double *d_alpha, const double *x, double *out, size_t n, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    int sms = 0;
+    LB_TRY(sm_count(&sms));
+    k_axpy<false><<<pick_grid((long long)n, sms, 0), kThreads, 0, st>>>(d_alpha, x, nullptr, out, (long long)n);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int lbfgsb200_eval_trial(int objective, const double *x, const double *d, const double *d_alpha,
+                         size_t n, double *g_out, double *d_out3, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch sc;
+    LB_TRY(sc.init((long long)n, st, 0, kCtasPerSmAccept));
+    k_eval_explicit<<<sc.grid, kThreads, 0, st>>>(MODE_TRIAL, objective, x, d, d_alpha, (long long)n,
+                                                   g_out, nullptr, nullptr, nullptr, nullptr, sc.p);
+    k_finalize<<<1, kScalarThreads, 0, st>>>(sc.p, sc.grid, 3, d_out3, 0);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int lbfgsb200_accept(int objective, double *x, const double *d, double *g, const double *d_alpha,
+                     size_t n, double *s_out, double *y_out, double *d_out5, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch sc;
+    const size_t stride = (n + 31) / 32 * 32;
+    LB_TRY(sc.init((long long)n, st, stride, kCtasPerSmAccept));
+    double *x_new = sc.extra(); // the kernel never writes the new iterate over x (see kernels.cuh)
+    k_eval_explicit<<<sc.grid, kThreads, 0, st>>>(MODE_ACCEPT, objective, x, d, d_alpha, (long long)n,
+                                                   nullptr, x_new, g, s_out, y_out, sc.p);
+    k_finalize<<<1, kScalarThreads, 0, st>>>(sc.p, sc.grid, 5, d_out5, 0);
+    CUDA_TRY(cudaMemcpyAsync(x, x_new, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// helper kernels of lbfgsb200_two_loop: fill the per-slot scalars of a scratch DevState from
+// two dot products, then run the production direction phase on it
+__global__ void k_set_pair(DevState *st, int slot)
+{
+    __shared__ double r[kMaxQ];
+    reduce_partials(st->partials, st->grid, 2, r);
+    if (threadIdx.x == 0) {
+        st->sy[slot] = r[0];
+        st->yy[slot] = r[1];
+        st->rho[slot] = 1.0 / r[0];
+        st->skip[slot] = 0;
+    }
+}
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+k_pair_dots(const double *__restrict__ s, const double *__restrict__ y, long long n, double *partials)
+{
+    double a0 = 0.0, a1 = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        a0 += s[i] * y[i];
+        a1 += y[i] * y[i];
+    }
+    double v[2] = {a0, a1};
+    block_emit<2>(v, partials);
+}
+__global__ void k_two_loop_out(const DevState *st, double *d_out2)
+{
+    d_out2[0] = st->gd;
+    d_out2[1] = (double)st->steepest;
+}
+
+__global__ void k_set_gg(DevState *st)
+{
+    __shared__ double r[kMaxQ];
+    reduce_partials(st->partials, st->grid, 1, r);
+    if (threadIdx.x == 0) st->gg = r[0];
+}
+
+int lbfgsb200_two_loop(const double *g, const double *S, const double *Y, int h, size_t n,
+                       size_t stride, double *d, double *d_out2, void *stream)
+{
+    if (h < 0 || h > LBFGSB200_MAX_M) { set_error("two_loop: h out of range"); return LBFGSB200_ERR_INVALID; }
+    cudaStream_t stream_ = (cudaStream_t)stream;
+    lbfgsb200_solver tmp; // borrowed launch context: owns nothing
+    memset(&tmp.params, 0, sizeof tmp.params);
+    tmp.stream = stream_;
+    LB_TRY(sm_count(&tmp.sms));
+    tmp.grid = pick_grid((long long)n, tmp.sms, 0);
+    tmp.params.m = h > 0 ? h : 1;
+    tmp.k_host = h;
+    double *partials = nullptr;
+    DevState *d_st = nullptr;
+    CUDA_TRY(cudaMallocAsync(&partials, sizeof(double) * kMaxQ * (size_t)tmp.grid, stream_));
+    CUDA_TRY(cudaMallocAsync(&d_st, sizeof(DevState), stream_));
+    DevState st;
+    memset(&st, 0, sizeof st);
+    st.n = (long long)n;
+    st.nglob = (long long)n;
+    st.m = tmp.params.m;
+    st.nslots = st.m + 1;
+    st.profile = LBFGSB200_PROFILE_SEQ;
+    st.max_iterations = 1 << 30;
+    st.tolerance = 0.0;
+    st.nranks = 1;
+    st.grid = tmp.grid;
+    st.g = const_cast<double *>(g);
+    st.w = d;
+    st.S = const_cast<double *>(S);
+    st.Y = const_cast<double *>(Y);
+    st.stride = (long long)stride;
+    st.partials = partials;
+    st.h = h;
+    st.k = 1;        // not the first iteration: use the history
+    st.sg_valid = 0; // exercises the stand-alone s.g path
+    CUDA_TRY(cudaMemcpyAsync(d_st, &st, sizeof st, cudaMemcpyHostToDevice, stream_));
+    CUDA_TRY(cudaStreamSynchronize(stream_)); // st is a stack object
+    k_dot<<<tmp.grid, kThreads, 0, stream_>>>(g, g, (long long)n, partials);
+    k_set_gg<<<1, kScalarThreads, 0, stream_>>>(d_st);
+    for (int i = 0; i < h; ++i) {
+        k_pair_dots<<<tmp.grid, kThreads, 0, stream_>>>(S + (size_t)i * stride, Y + (size_t)i * stride, (long long)n, partials);
+        k_set_pair<<<1, kScalarThreads, 0, stream_>>>(d_st, i);
+    }
+    tmp.d_st = d_st;
+    int rc = launch_direction(&tmp);
+    k_two_loop_out<<<1, 1, 0, stream_>>>(d_st, d_out2);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(partials, stream_);
+    cudaFreeAsync(d_st, stream_);
+    if (rc < 0) return rc;
+    if (e != cudaSuccess) { set_error("two_loop launch: %s", cudaGetErrorString(e)); return LBFGSB200_ERR_CUDA; }
+    return 0;
+}
+
+// pinned host buffers for callers without their own CUDA runtime access (the Python harness)
+void *lbfgsb200_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        set_error("cudaHostAlloc(%zu) failed", bytes);
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void lbfgsb200_host_free(void *p) { if (p) cudaFreeHost(p); }
+void *lbfgsb200_device_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        set_error("cudaMalloc(%zu) failed", bytes);
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void lbfgsb200_device_free(void *p) { if (p) cudaFree(p); }
+int lbfgsb200_memcpy(void *dst, const void *src, size_t bytes)
+{
+    CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+    return 0;
+}
+int lbfgsb200_set_device(int ordinal)
+{
+    CUDA_TRY(cudaSetDevice(ordinal));
+    return 0;
+}
+int lbfgsb200_device_sync(void)
+{
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+} // extern "C"

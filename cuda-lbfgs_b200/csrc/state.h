@@ -1,0 +1,121 @@
+// state.h -- device-resident solver state shared by every kernel.
+//
+// The whole iteration is driven from this struct: ring-buffer slot arithmetic, the
+// rho/alpha/beta scalars of the two-loop recursion, the line-search state machine and the
+// exit flags all live in HBM, are written by the 1-CTA scalar kernel (scalar_ops.cuh) and
+// read by the streaming kernels (kernels.cuh).  The host never needs a scalar to decide
+// what to launch next except the 16-byte `ctrl` block in host-stepped mode.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/lbfgsb200.h"
+#include "ls_logic.h"
+
+namespace lb {
+
+constexpr int kMaxM = LBFGSB200_MAX_M;
+constexpr int kMaxSlots = kMaxM + 1; // one spare slot: the candidate pair is written there and
+                                     // only committed when the profile's curvature gate passes
+constexpr int kThreads = 256;        // streaming kernels: 256 threads, 4 CTAs / SM
+constexpr int kCtasPerSm = 4;
+constexpr int kCtasPerSmAccept = 2;  // the 7-stream accept kernel trades occupancy for registers
+constexpr int kUnroll = 4;           // double2 items per thread per tile
+constexpr int kTileVec = kThreads * kUnroll; // 1024 double2 = 16 KB per stream per tile
+constexpr int kMaxQ = 8;             // partial sums one kernel may emit
+constexpr int kPacket = 12;          // doubles per rank in the packed per-step exchange
+constexpr int kMaxRanks = 16;
+
+// scalar-kernel opcodes
+enum Op : int {
+    OP_INIT = 0,     // after the x0 evaluation
+    OP_ITER_BEGIN,   // convergence test, steepest-descent decision, first alpha
+    OP_SG,           // (rare) finalise s_newest . g when the last pair was not committed
+    OP_L1,           // after loop-1 pass p
+    OP_L2,           // after loop-2 pass p
+    OP_LS_INIT,      // descent safeguard + line-search start
+    OP_LS_STEP,      // one line-search decision
+    OP_ACCEPT,       // after the accept/update kernel
+    OP_COMPACT,      // compact form: Gram update + coefficient recursion
+    OP_COMPACT_DIR,  // after the compact direction kernel (g.d)
+};
+
+// 16-byte block the host reads back once per trial in host-stepped mode
+struct Ctrl {
+    int ls_active;
+    int done;
+    int h;
+    int k;
+};
+
+struct DevState {
+    // ---- immutable after create ----
+    long long n;      // local elements
+    long long goff;   // global index of local element 0
+    long long nglob;  // global problem size
+    int m, nslots;
+    int objective, profile, direction;
+    int max_iterations;
+    double tolerance;
+    int rank, nranks;
+    int grid;         // CTAs of the 4-per-SM streaming kernels (partial count is passed per launch)
+    int grid_accept;  // CTAs of the accept kernel
+    double *x, *x_alt, *g, *w; // w: two-loop work vector q/r, ends as the direction d;
+                               // x_alt: the accept kernel writes the new iterate here, then x <-> x_alt
+    double *S, *Y;     // ring buffers, nslots rows of `stride` doubles
+    long long stride;
+    double *partials;  // [kMaxQ][grid]
+    double *send, *recv; // multi-GPU packet buffers: [kPacket], [nranks][kPacket]
+    double *trace;
+    long long trace_rows;
+    LsParams lsp;
+
+    // ---- ring ----
+    int base; // physical slot of the oldest pair
+    int h;    // stored pairs
+    double rho[kMaxSlots]; // per physical slot: 1/(s.y)
+    double sy[kMaxSlots];
+    double yy[kMaxSlots];
+    unsigned char skip[kMaxSlots]; // CUDA profile: pair excluded (s.y <= 1e-10)
+
+    // ---- direction ----
+    double alpha[kMaxM]; // per window position (0 = oldest)
+    double coef;         // coefficient of the next streaming pass
+    double gscale;       // gamma on the first loop-2 pass / last loop-1 dot, else 1.0
+    double gamma;
+    double sg;           // s_newest . g (from the accept kernel when the pair was committed)
+    int sg_valid;
+    int need_sg;
+    int steepest;
+
+    // ---- iterate ----
+    double f, gg, gd;
+    int k;
+    int status;
+    Ctrl ctrl;
+    long long trial_evals;
+
+    // ---- line search ----
+    LsState ls;
+
+    // ---- halo (multi-GPU, neighbour-coupled objectives) ----
+    // boundary values of the neighbours' shards, refreshed once per outer iteration
+    double xL, xR, dL, dR, gL, gR;
+
+    // ---- accounting: algorithmic HBM traffic in units of one local vector (8 n bytes) ----
+    double vec_streams;
+
+    // ---- compact form (separate allocations; see compact.cuh) ----
+    double *gram;  // Gram matrix of the basis [s slots, y slots, g]
+    double *delta; // direction coefficients on that basis
+};
+
+__host__ __device__ inline int slot_of(const DevState &st, int pos)
+{
+    return (st.base + pos) % st.nslots;
+}
+__host__ __device__ inline int spare_slot(const DevState &st)
+{
+    return (st.base + st.h) % st.nslots;
+}
+
+} // namespace lb

@@ -1,0 +1,214 @@
+/*
+ * lbfgsb200.h -- C ABI of the B200-native FP64 L-BFGS hot path.
+ *
+ * Drop-in boundary for the solver surface of ndzajic1/cuda-lbfgs.  Every entry
+ * point cites the reference interface it replaces:
+ *   seq/ = sequential-implementation/, par/ = parallel-implementation/.
+ *
+ * Plain C: pointers, sizes, PODs.  No torch / STL types.  All device work runs
+ * in hand-written sm_100a kernels; there is NO CPU fallback: on a machine
+ * without a usable CUDA device every compute entry point fails with
+ * LBFGSB200_ERR_CUDA.
+ *
+ * The C++ shim with the reference's exact `LBFGS(f, grad, x0, method, ...)`
+ * signature is include/lbfgsb200_compat.hpp.
+ */
+#ifndef LBFGSB200_H
+#define LBFGSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBFGSB200_VERSION 100
+#define LBFGSB200_MAX_M 64        /* history pairs (reference default m=10; sweep goes to 50) */
+#define LBFGSB200_TRACE_COLS 8
+#define LBFGSB200_UNIQUE_ID_BYTES 128
+
+/* line searches selectable by name in the reference: seq/lbfgs.cpp:40-70 */
+typedef enum {
+    LBFGSB200_LS_BACKTRACKING = 0,      /* seq/line_search.cpp:19-30,  par/line_search.cpp:25-43  */
+    LBFGSB200_LS_INTERPOLATION = 1,     /* seq/line_search.cpp:57-121, par/line_search.cpp:156-228 */
+    LBFGSB200_LS_WOLFE = 2,             /* seq/line_search.cpp:125-189, par/line_search.cpp:298-369 */
+    LBFGSB200_LS_BACKTRACKING_WOLFE = 3 /* seq/line_search.cpp:33-55,  par/line_search.cpp:45-154 */
+} lbfgsb200_ls_t;
+
+/* which tree's line-search code and constants are followed:
+ * SEQ = seq/line_search.cpp + seq/config.h (C2=0.9, cubicInterpolate),
+ * PAR = par/line_search.cpp + par/constants.h (C2=0.7, safeCubicInterpolate, 0.5 floor) */
+typedef enum { LBFGSB200_FLAVOR_SEQ = 0, LBFGSB200_FLAVOR_PAR = 1 } lbfgsb200_flavor_t;
+
+/* outer-loop semantics:
+ * SEQ  = seq/lbfgs.cpp:72-199 (test ||g||<tol before the step, store a pair only if s.y>0,
+ *        non-finite rho / bad gamma / non-descent => d=-g),
+ * CUDA = par/L-BFGS*.cu (ring slot always overwritten, pairs with s.y<=1e-10 skipped,
+ *        gamma fallback 1.0, test ||g||<=tol after the step, no descent safeguard) */
+typedef enum { LBFGSB200_PROFILE_SEQ = 0, LBFGSB200_PROFILE_CUDA = 1 } lbfgsb200_profile_t;
+
+/* search-direction algorithm: explicit two-loop (seq/lbfgs.cpp:93-143) or the
+ * compact / Gram form that reads all 2m history vectors once */
+typedef enum { LBFGSB200_DIR_TWO_LOOP = 0, LBFGSB200_DIR_COMPACT = 1 } lbfgsb200_dir_t;
+
+/* built-in device objectives: par/functions.cpp:6-49, seq/benchmark.cpp:16-56 */
+typedef enum {
+    LBFGSB200_OBJ_QUADRATIC = 0,
+    LBFGSB200_OBJ_ROSENBROCK = 1,
+    LBFGSB200_OBJ_TRIDIAG = 2
+} lbfgsb200_obj_t;
+
+typedef enum {
+    LBFGSB200_CONVERGED = 0,       /* "Converged!"                 seq/lbfgs.cpp:82  */
+    LBFGSB200_MAX_ITER = 1,        /* "Maximum iterations reached" seq/lbfgs.cpp:201 */
+    LBFGSB200_LS_FAILED = 2,       /* "Line search failed"         seq/lbfgs.cpp:166 */
+    LBFGSB200_RUNNING = 3,         /* iterate() returned before any exit condition */
+    LBFGSB200_ERR_INVALID = -1,    /* std::invalid_argument in the reference (seq/lbfgs.cpp:69) */
+    LBFGSB200_ERR_CUDA = -2,       /* checkCudaError + exit(1) in the reference (par/L-BFGS.cu:76-83) */
+    LBFGSB200_ERR_NCCL = -3,
+    LBFGSB200_ERR_NOMEM = -4
+} lbfgsb200_status_t;
+
+/* Replaces the reference's positional arguments (seq/lbfgs.h:17-25: max_iterations,
+ * m, tolerance, line_search_method) and its compile-time constants
+ * (seq/config.h:5-17, par/constants.h:5-21). */
+typedef struct {
+    int m;               /* history size, 1..LBFGSB200_MAX_M */
+    int max_iterations;
+    double tolerance;
+    int line_search;     /* lbfgsb200_ls_t */
+    int flavor;          /* lbfgsb200_flavor_t */
+    int profile;         /* lbfgsb200_profile_t */
+    int direction;       /* lbfgsb200_dir_t */
+    double c1;           /* C1 */
+    double c2;           /* C2 */
+    double step0;        /* INITIAL_STEP_SIZE */
+    double shrink;       /* BACKTRACKING_ALPHA */
+    double backtracking_tol; /* BACKTRACKING_TOL */
+    double wolfe_min;    /* WOLFE_INTERP_MIN */
+    int ls_max_trials;   /* 20 in the reference (seq/line_search.cpp:73, :143) */
+    int use_graph;       /* 1: whole iteration loop runs as one CUDA graph (device-side control flow) */
+    int verbose;         /* 1: print the reference's per-iteration line (seq/lbfgs.cpp:77-78) from the trace */
+    int grid_ctas;       /* 0 = auto (4 CTAs x SM count); tuning/testing knob */
+} lbfgsb200_params_t;
+
+typedef struct {
+    int status;          /* lbfgsb200_status_t */
+    int64_t iterations;  /* completed steps */
+    int64_t trial_evals; /* fused line-search evaluations launched */
+    int64_t kernel_launches;
+    double f;            /* f at the returned x */
+    double gnorm;        /* ||grad f|| at the returned x */
+    double device_ms;    /* CUDA-event time of the last iterate()/solve() device region */
+    double bytes_moved;  /* algorithmic HBM bytes of that region (bytes model) */
+} lbfgsb200_result_t;
+
+typedef struct lbfgsb200_solver lbfgsb200_solver_t; /* one per GPU / rank */
+typedef struct lbfgsb200_comm lbfgsb200_comm_t;     /* NCCL communicator wrapper */
+
+/* ------------------------------------------------------------------ */
+/* library                                                             */
+/* ------------------------------------------------------------------ */
+int lbfgsb200_version(void);
+const char *lbfgsb200_strerror(int status);
+const char *lbfgsb200_last_error(void); /* thread-local detail string of the last failure */
+int lbfgsb200_device_count(void);       /* 0 when no CUDA device is usable */
+
+/* defaults = the reference's constants for the given line-search tree
+ * (seq/config.h or par/constants.h) and lbfgs.h defaults (m=10, max_it=1000, tol=1e-5) */
+int lbfgsb200_params_default(lbfgsb200_params_t *p, int flavor);
+
+/* ------------------------------------------------------------------ */
+/* solver: replaces LBFGS() seq/lbfgs.cpp:17-203 and LBFGS_CUDA()      */
+/* par/L-BFGS.cu:105-382 (+ the four inlined-line-search variants)     */
+/* ------------------------------------------------------------------ */
+
+/* One-shot, host buffers in and out (the reference's by-value vector<double> x0 and
+ * returned vector<double>).  trace may be NULL; rows of LBFGSB200_TRACE_COLS doubles:
+ * k, f, ||g||, alpha, trials, history size, x[0], x[n/2]. */
+int lbfgsb200_solve(int objective, size_t n, const double *x0_host, double *x_out_host,
+                    const lbfgsb200_params_t *params, lbfgsb200_result_t *result,
+                    double *trace, size_t trace_rows);
+
+/* Resumable form.  n_global is the full problem size; with comm != NULL this rank owns the
+ * contiguous shard given by lbfgsb200_shard_range(n_global, rank, nranks). */
+int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
+                     const lbfgsb200_params_t *params, lbfgsb200_comm_t *comm,
+                     size_t trace_rows);
+/* x0: this rank's shard (n_local doubles), host or device pointer.  Evaluates f(x0), grad f(x0)
+ * (seq/lbfgs.cpp:28-30). */
+int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local);
+/* Runs at most `iterations` further steps (or until converged / failed / max_iterations). */
+int lbfgsb200_iterate(lbfgsb200_solver_t *s, int64_t iterations);
+/* As iterate(), but forces the host-stepped path and records a CUDA-event pair around every
+ * streaming kernel.  class_ms[0..3] / class_launches[0..3] receive the summed device time and
+ * launch count of: 0 two-loop passes, 1 trial evaluations, 2 accept/update, 3 everything else. */
+int lbfgsb200_iterate_profiled(lbfgsb200_solver_t *s, int64_t iterations, double class_ms[4],
+                               int64_t class_launches[4]);
+int lbfgsb200_get_x(lbfgsb200_solver_t *s, double *x_local_out); /* host or device pointer */
+int lbfgsb200_get_result(lbfgsb200_solver_t *s, lbfgsb200_result_t *r);
+int64_t lbfgsb200_get_trace(lbfgsb200_solver_t *s, double *rows, size_t max_rows);
+size_t lbfgsb200_local_size(const lbfgsb200_solver_t *s);
+void lbfgsb200_destroy(lbfgsb200_solver_t *s);
+
+/* Contiguous shard of rank r: every rank owns (n / nranks) rounded down to an even count, the
+ * last rank takes the remainder, so each shard starts on a 16-byte boundary of the global
+ * vector.  Pure host arithmetic (no CUDA needed). */
+void lbfgsb200_shard_range(size_t n_global, int rank, int nranks, size_t *offset, size_t *n_local);
+
+/* ------------------------------------------------------------------ */
+/* multi-GPU plumbing (new work; the reference has none)               */
+/* ------------------------------------------------------------------ */
+int lbfgsb200_comm_unique_id(char id[LBFGSB200_UNIQUE_ID_BYTES]);
+int lbfgsb200_comm_create(lbfgsb200_comm_t **out, const char id[LBFGSB200_UNIQUE_ID_BYTES],
+                          int rank, int nranks);
+void lbfgsb200_comm_destroy(lbfgsb200_comm_t *c);
+
+/* ------------------------------------------------------------------ */
+/* unit-test surface: the vector_utils / kernel layer.  Device pointers */
+/* in, results left in DEVICE scalars (no host sync).  stream is a      */
+/* cudaStream_t passed as void*.                                        */
+/* ------------------------------------------------------------------ */
+/* dotProduct  seq/vector_utils.cpp:32-41 ; cublasDdot sites par/L-BFGS.cu:219-267 */
+int lbfgsb200_dot(const double *a, const double *b, size_t n, double *d_out, void *stream);
+/* vectorNorm  seq/vector_utils.cpp:78-86 ; par/L-BFGS.cu:346-347 */
+int lbfgsb200_nrm2(const double *a, size_t n, double *d_out, void *stream);
+/* y += alpha*x with alpha read from a device scalar; cublasDaxpy sites par/L-BFGS.cu:233,:272 */
+int lbfgsb200_axpy(const double *d_alpha, const double *x, double *y, size_t n, void *stream);
+/* scalarProduct seq/vector_utils.cpp:43-51 ; scaleByRho par/L-BFGS.cu:65-73 ; out may alias x */
+int lbfgsb200_scal(const double *d_alpha, const double *x, double *out, size_t n, void *stream);
+/* Fused trial evaluation at x + alpha*d without materialising it (replaces updateSolution +
+ * host f/grad + ddot, par/L-BFGS-Wolfe.cu:276-311).  g_out may be NULL.  d_out3 receives
+ * f, grad.d, grad.grad. */
+int lbfgsb200_eval_trial(int objective, const double *x, const double *d, const double *d_alpha,
+                         size_t n, double *g_out, double *d_out3, void *stream);
+/* Two-loop recursion (seq/lbfgs.cpp:93-143) over h pairs stored oldest first as rows of S and Y
+ * (row stride `stride` doubles, 16-byte aligned rows).  Writes d; d_out2 = {g.d, fell_back}. */
+int lbfgsb200_two_loop(const double *g, const double *S, const double *Y, int h, size_t n,
+                       size_t stride, double *d, double *d_out2, void *stream);
+/* Accept step (updateSolution + updateVectors, par/L-BFGS.cu:55-63, :19-31, + grad):
+ * x += alpha d, g = grad f(x), s = x_new - x, y = g_new - g ; d_out5 = f, g.g, s.y, y.y, s.g */
+int lbfgsb200_accept(int objective, double *x, const double *d, double *g, const double *d_alpha,
+                     size_t n, double *s, double *y, double *d_out5, void *stream);
+
+/* Host helper: x0 exactly as the reference mains draw it -- std::mt19937(seed) +
+ * std::uniform_real_distribution<>(lo,hi), sequentially (seq/main.cpp:34-43,
+ * par/L-BFGS-Wolfe.cu:458-465).  Writes elements [offset, offset+count). */
+void lbfgsb200_x0_uniform(unsigned seed, double lo, double hi, size_t offset, size_t count,
+                          double *out_host);
+
+/* Raw CUDA-runtime helpers for hosts that do not link the CUDA runtime themselves (the
+ * ctypes harness): pinned host buffers, device buffers, copies, device selection. */
+void *lbfgsb200_host_alloc(size_t bytes);
+void lbfgsb200_host_free(void *p);
+void *lbfgsb200_device_alloc(size_t bytes);
+void lbfgsb200_device_free(void *p);
+int lbfgsb200_memcpy(void *dst, const void *src, size_t bytes);
+int lbfgsb200_set_device(int ordinal);
+int lbfgsb200_device_sync(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBFGSB200_H */

@@ -1,0 +1,151 @@
+"""CPU: host-side logic of the product, no GPU needed.
+
+* the line-search state machines (csrc/ls_logic.h, the code the GPU scalar kernel runs) built for
+  the host and compared bit-for-bit with the oracle's restatement of the reference loops;
+* the C-ABI library loads and exports every symbol include/lbfgsb200.h declares;
+* params defaults, shard arithmetic, the x0 generator; loud failure without a device.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+LS = ["backtracking", "interpolation", "wolfe", "backtracking_wolfe"]
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("ls") / "libls_harness.so")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++14", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
+                           os.path.join(ROOT, "tests", "ls_harness.cpp"), "-o", out])
+    L = C.CDLL(out)
+    L.harness_ls_poly.restype = C.c_double
+    L.harness_ls_poly.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    for n, k in (("harness_cubic", 6), ("harness_safe_cubic", 6), ("harness_quadratic", 4)):
+        getattr(L, n).restype = C.c_double
+        getattr(L, n).argtypes = [C.c_double] * k
+    return L
+
+
+def _same(a, b):
+    return a == b or (np.isnan(a) and np.isnan(b))
+
+
+def test_line_search_state_machines_match_oracle(harness, oracle):
+    rng = np.random.default_rng(11)
+    n_checked = 0
+    for trial in range(4000):
+        # descent at 0 (c1 < 0), varied curvature so every branch fires: accepts, shrinks,
+        # bracket moves, expansions (hi = inf), NaN-producing cubics
+        scale = 10.0 ** rng.integers(-3, 4)
+        coef = np.array([rng.normal() * scale, -abs(rng.normal()) * scale, rng.normal() * scale * 2,
+                         rng.normal() * scale * (trial % 3 == 0), abs(rng.normal()) * scale * (trial % 5 == 0)])
+        for kind, ls in enumerate(LS):
+            for flavor, fl in enumerate(("seq", "par")):
+                want, nf, ng = oracle.ls_poly(ls, fl, coef)
+                tr = C.c_int(0)
+                got = harness.harness_ls_poly(kind, flavor, coef.ctypes.data_as(C.POINTER(C.c_double)), C.byref(tr))
+                assert _same(got, want), (ls, fl, coef, got, want)
+                n_checked += 1
+    assert n_checked == 4000 * 8
+
+
+def test_line_search_trial_counts(harness, oracle):
+    # phi(a) = 1 - a + 50 a^2 : steep valley, forces several shrink steps
+    coef = np.array([1.0, -1.0, 50.0, 0.0, 0.0])
+    p = coef.ctypes.data_as(C.POINTER(C.c_double))
+    tr = C.c_int(0)
+    a = harness.harness_ls_poly(0, 0, p, C.byref(tr))
+    want, nf, ng = oracle.ls_poly("backtracking", "seq", coef)
+    assert a == want and nf == 2 * tr.value  # the reference evaluates f(x) AND f(x+ad) per test
+    a = harness.harness_ls_poly(2, 1, p, C.byref(tr))
+    want, nf, ng = oracle.ls_poly("wolfe", "par", coef)
+    assert a == want and nf == tr.value + 1 and ng <= tr.value
+
+
+def test_interpolation_helpers_match_oracle(harness, oracle):
+    rng = np.random.default_rng(5)
+    for _ in range(20000):
+        a = rng.uniform(-3, 3, 6) * 10.0 ** rng.integers(-2, 3)
+        assert _same(harness.harness_cubic(*a), oracle.cubic(*a))
+        assert _same(harness.harness_safe_cubic(*a), oracle.safe_cubic(*a))
+        assert _same(harness.harness_quadratic(a[0], a[2], a[3], a[4]), oracle.quadratic_interp(a[0], 0.0, a[2], a[3], a[4]))
+    # degenerate brackets
+    for args in ((0, 0, 1, -1, 1, 1), (1, 0, 2, -1, 3, 1), (0, 1, 1, 0, 1, 0), (0, np.inf, 1, -1, 2, 1)):
+        assert _same(harness.harness_safe_cubic(*args), oracle.safe_cubic(*args))
+        assert _same(harness.harness_cubic(*args), oracle.cubic(*args))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    L = pkg.lib()
+    header = open(os.path.join(ROOT, "include", "lbfgsb200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(lbfgsb200_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(L, name), "library does not export " + name
+    assert sorted(pkg.EXPORTS) == declared
+    assert L.lbfgsb200_version() == 100
+
+
+def test_library_is_sm100a_native(pkg):
+    """The shipped library carries sm_100a SASS for the hot kernels (built by nvcc, not JIT)."""
+    pkg.lib()
+    r = subprocess.run(["cuobjdump", "-lelf", pkg.LIB_PATH], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    assert "sm_100a" in r.stdout
+
+
+def test_params_defaults_are_the_reference_constants(pkg):
+    p = pkg.default_params("seq")
+    assert (p.m, p.max_iterations, p.tolerance) == (10, 1000, 1e-5)  # seq/lbfgs.h:22-24
+    assert (p.c1, p.c2, p.step0, p.shrink) == (1e-4, 0.9, 1.0, 0.5)   # seq/config.h
+    assert (p.backtracking_tol, p.wolfe_min, p.ls_max_trials) == (1e-8, 1e-10, 20)
+    assert pkg.default_params("par").c2 == 0.7                        # par/constants.h:6
+
+
+def test_shard_ranges_cover_and_align(pkg):
+    for n in (1, 2, 3, 17, 10000, 10001, 10 ** 8, 2 * 10 ** 9 + 1):
+        for P in (1, 2, 3, 4, 8):
+            if n < 2 * P and P > 1:
+                continue
+            pos = 0
+            for r in range(P):
+                off, ln = pkg.shard_range(n, r, P)
+                assert off == pos and ln > 0
+                assert off % 2 == 0  # every shard starts on a 16-byte boundary
+                pos += ln
+            assert pos == n
+
+
+def test_x0_generator_matches_oracle(pkg, oracle):
+    for lo, hi in ((-2, 2), (-1000, 1000), (0.5, 1.5)):
+        a = pkg.x0_uniform(1000, lo, hi)
+        assert np.array_equal(a, oracle.x0(1000, lo, hi))
+        b = pkg.x0_uniform(100, lo, hi, offset=900)
+        assert np.array_equal(b, a[900:])  # shards can be generated independently
+
+
+def test_invalid_arguments_are_rejected(pkg):
+    p = pkg.default_params("seq")
+    p.line_search = 7  # the reference throws invalid_argument("Unknown line search method")
+    with pytest.raises(pkg.LbfgsError, match="Unknown line search method"):
+        pkg.Solver("rosenbrock", 100, p)
+    p = pkg.default_params("seq", m=0)
+    with pytest.raises(pkg.LbfgsError):
+        pkg.Solver("rosenbrock", 100, p)
+
+
+def test_no_cpu_fallback(pkg):
+    """Without a CUDA device the solver must fail loudly, never compute on the CPU."""
+    if pkg.lib().lbfgsb200_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pkg.LbfgsError, match="no CPU fallback"):
+        pkg.solve("quadratic", np.zeros(16))
