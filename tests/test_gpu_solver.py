@@ -40,7 +40,9 @@ def test_traces_match_reference_golden(gpu, golden):
             for got, key in ((x[0], "x_first"), (x[n // 2], "x_mid"), (x[-1], "x_last")):
                 ref = unhex(want[key])
                 assert abs(got - ref) <= tol * max(abs(ref), 1e-3), (name, K, key, got, ref)
-            assert info["iterations"] == K and len(tr) == K
+            assert len(tr) == info["iterations"] <= K
+            if want["status"] == 1:  # "Maximum iterations reached": exactly K steps were taken
+                assert info["iterations"] == K
 
 
 def test_traces_match_oracle_every_iteration(gpu, oracle, golden):
