@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
            "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared",
            "-Xptxas", "-v" if verbose else "-O3"]
     cmd += [os.path.join(CSRC, f) for f in SOURCES]
-    cmd += ["-lnccl", "-o", LIB]
+    cmd += ["-ldl", "-o", LIB]  # NCCL is dlopen()ed at run time (csrc/comm.cpp)
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
