@@ -1,0 +1,217 @@
+// lbfgsb200_compat.hpp -- C++ shim: the reference's entry points on top of the C ABI.
+//
+// Defines, with the reference's exact signatures,
+//     vector<double> LBFGS(f, grad, x0, line_search_method, max_iterations, m, tolerance, verbose)
+//         -- sequential-implementation/lbfgs.h:17-25 (definition lbfgs.cpp:17-25)
+//     vector<double> LBFGS_CUDA(f, grad, x0, line_search_method, max_iterations, m, tolerance)
+//         -- parallel-implementation/L-BFGS.cu:105-112
+//     vector<double> LBFGS_CUDA(f, grad, x0, max_iterations, m, tolerance)
+//         -- parallel-implementation/L-BFGS-Wolfe.cu:105-111 (and the other inlined variants)
+// so that the reference's own callers (sequential-implementation/main.cpp + benchmark.cpp, the
+// main() of each parallel-implementation/*.cu) link against liblbfgsb200.so unchanged.
+//
+// Usage: compile ONE translation unit with
+//     #define LBFGSB200_COMPAT_IMPLEMENTATION
+//     #include "lbfgsb200_compat.hpp"
+// next to the unmodified caller sources and link -llbfgsb200.  Callers keep including the
+// reference's own lbfgs.h (which carries the default arguments).
+//
+// Objectives: host std::function callbacks cannot run inside the device-resident iteration loop.
+// The shim identifies which built-in device objective a callback pair IS by evaluating it on two
+// fixed 6-element probe vectors and comparing f and grad bit-for-bit with the built-ins
+// (parallel-implementation/functions.cpp:6-49, sequential-implementation/benchmark.cpp:16-56).
+// Anything else throws std::invalid_argument -- there is deliberately no CPU fallback.
+#ifndef LBFGSB200_COMPAT_HPP
+#define LBFGSB200_COMPAT_HPP
+
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "lbfgsb200.h"
+
+namespace lbfgsb200 {
+struct CompatOptions {
+    int flavor = -1;          // -1: LBFGS -> SEQ tree, LBFGS_CUDA -> PAR tree
+    int profile = -1;         // -1: LBFGS -> SEQ outer loop, LBFGS_CUDA -> CUDA outer loop
+    int direction = LBFGSB200_DIR_TWO_LOOP;
+    int use_graph = 0;
+    const char *cuda_default_line_search = "wolfe"; // for the LBFGS_CUDA overload without a method
+    lbfgsb200_result_t last_result;                 // filled by every call (the reference only prints)
+};
+CompatOptions &compat_options();
+// returns LBFGSB200_OBJ_* or -1
+int identify_objective(const std::function<double(std::vector<double>)> &f,
+                       const std::function<std::vector<double>(std::vector<double>)> &grad);
+} // namespace lbfgsb200
+
+#ifdef LBFGSB200_COMPAT_IMPLEMENTATION
+
+#include <cstring>
+#include <iostream>
+#include <stdexcept>
+
+namespace lbfgsb200 {
+
+CompatOptions &compat_options()
+{
+    static CompatOptions o;
+    return o;
+}
+
+namespace detail {
+// the built-ins on a tiny host vector, for identification only
+inline double builtin_f(int obj, const std::vector<double> &x)
+{
+    const size_t n = x.size();
+    double s = 0.0;
+    if (obj == LBFGSB200_OBJ_QUADRATIC) {
+        for (double v : x) s += (v - 1) * (v - 1);
+    } else if (obj == LBFGSB200_OBJ_ROSENBROCK) {
+        for (size_t i = 0; i + 1 < n; ++i) {
+            double t1 = x[i + 1] - x[i] * x[i], t2 = 1 - x[i];
+            s += 100.0 * t1 * t1 + t2 * t2;
+        }
+    } else {
+        for (size_t i = 0; i < n; ++i) s += 1000.0 * x[i] * x[i];
+        for (size_t i = 0; i + 1 < n; ++i) s += (1000.0 / 10.0) * x[i] * x[i + 1];
+    }
+    return s;
+}
+inline std::vector<double> builtin_g(int obj, const std::vector<double> &x)
+{
+    const size_t n = x.size();
+    std::vector<double> g(n, 0.0);
+    if (obj == LBFGSB200_OBJ_QUADRATIC) {
+        for (size_t i = 0; i < n; ++i) g[i] = 2.0 * (x[i] - 1);
+    } else if (obj == LBFGSB200_OBJ_ROSENBROCK) {
+        for (size_t i = 0; i + 1 < n; ++i) {
+            double t1 = 2.0 * (x[i] - 1), t2 = x[i + 1] - x[i] * x[i];
+            g[i] += t1 - 400.0 * x[i] * t2;
+            g[i + 1] += 200.0 * t2;
+        }
+    } else {
+        for (size_t i = 0; i < n; ++i) g[i] = 2.0 * 1000.0 * x[i];
+        for (size_t i = 0; i + 1 < n; ++i) {
+            g[i] += (1000.0 / 10.0) * x[i + 1];
+            g[i + 1] += (1000.0 / 10.0) * x[i];
+        }
+    }
+    return g;
+}
+inline bool close(double a, double b)
+{
+    double d = a > b ? a - b : b - a, m = (a < 0 ? -a : a) + (b < 0 ? -b : b);
+    return d <= 1e-12 * m + 1e-300;
+}
+} // namespace detail
+
+int identify_objective(const std::function<double(std::vector<double>)> &f,
+                       const std::function<std::vector<double>(std::vector<double>)> &grad)
+{
+    const std::vector<double> probes[2] = {{0.3, -1.2, 0.7, 1.9, -0.4, 1.1},
+                                           {1.5, 0.25, -0.8, 0.05, 2.2, -1.7}};
+    for (int obj = LBFGSB200_OBJ_QUADRATIC; obj <= LBFGSB200_OBJ_TRIDIAG; ++obj) {
+        bool ok = true;
+        for (const auto &p : probes) {
+            double fv;
+            std::vector<double> gv;
+            try {
+                fv = f(p);
+                gv = grad(p);
+            } catch (...) { // e.g. the tridiagonal generator asserts on the dimension
+                ok = false;
+                break;
+            }
+            if (!detail::close(fv, detail::builtin_f(obj, p)) || gv.size() != p.size()) { ok = false; break; }
+            const std::vector<double> want = detail::builtin_g(obj, p);
+            for (size_t i = 0; i < p.size(); ++i)
+                if (!detail::close(gv[i], want[i])) ok = false;
+            if (!ok) break;
+        }
+        if (ok) return obj;
+    }
+    return -1;
+}
+
+namespace detail {
+inline std::vector<double> run(const std::function<double(std::vector<double>)> &f,
+                               const std::function<std::vector<double>(std::vector<double>)> &grad,
+                               const std::vector<double> &x0, const std::string &method, int max_iterations,
+                               int m, double tolerance, bool verbose, bool cuda_entry)
+{
+    CompatOptions &o = compat_options();
+    int ls;
+    if (method == "backtracking") ls = LBFGSB200_LS_BACKTRACKING;
+    else if (method == "interpolation") ls = LBFGSB200_LS_INTERPOLATION;
+    else if (method == "wolfe") ls = LBFGSB200_LS_WOLFE;
+    else if (method == "backtracking_wolfe") ls = LBFGSB200_LS_BACKTRACKING_WOLFE;
+    else throw std::invalid_argument("Unknown line search method: " + method); // seq/lbfgs.cpp:69
+    const int obj = identify_objective(f, grad);
+    if (obj < 0)
+        throw std::invalid_argument(
+            "lbfgsb200: the objective is not one of the built-in device objectives (quadratic, rosenbrock, "
+            "tridiagonal quadratic); host callbacks cannot run on the GPU and there is no CPU fallback");
+    lbfgsb200_params_t p;
+    const int flavor = o.flavor >= 0 ? o.flavor : (cuda_entry ? LBFGSB200_FLAVOR_PAR : LBFGSB200_FLAVOR_SEQ);
+    lbfgsb200_params_default(&p, flavor);
+    p.profile = o.profile >= 0 ? o.profile : (cuda_entry ? LBFGSB200_PROFILE_CUDA : LBFGSB200_PROFILE_SEQ);
+    p.direction = o.direction;
+    p.use_graph = o.use_graph;
+    p.line_search = ls;
+    p.max_iterations = max_iterations;
+    p.m = m;
+    p.tolerance = tolerance;
+    std::vector<double> x(x0.size());
+    std::vector<double> trace;
+    size_t rows = 0;
+    if (verbose) {
+        rows = (size_t)(max_iterations < 100000 ? max_iterations : 100000);
+        trace.resize(rows * LBFGSB200_TRACE_COLS + 1);
+    }
+    int rc = lbfgsb200_solve(obj, x0.size(), x0.data(), x.data(), &p, &o.last_result, rows ? trace.data() : nullptr, rows);
+    if (rc == LBFGSB200_ERR_INVALID) throw std::invalid_argument(lbfgsb200_last_error());
+    if (rc < 0) { // the reference prints the CUDA error and exit(EXIT_FAILURE)s (par/L-BFGS.cu:76-83)
+        std::cerr << "lbfgsb200: " << lbfgsb200_strerror(rc) << " (" << lbfgsb200_last_error() << ")" << std::endl;
+        throw std::runtime_error(lbfgsb200_last_error());
+    }
+    if (verbose)
+        for (int64_t k = 0; k < o.last_result.iterations && (size_t)k < rows; ++k)
+            std::cout << "Iteration " << k + 1 << ", f = " << trace[k * LBFGSB200_TRACE_COLS + 1]
+                      << ", |grad| = " << trace[k * LBFGSB200_TRACE_COLS + 2] << std::endl;
+    // the reference's only status channel is stdout (seq/lbfgs.cpp:82, :166, :201)
+    if (rc == LBFGSB200_CONVERGED) std::cout << "Converged!" << std::endl;
+    else if (rc == LBFGSB200_LS_FAILED) std::cout << "Warning: Line search failed at iteration " << o.last_result.iterations << std::endl;
+    else std::cout << "Maximum iterations reached" << std::endl;
+    return x;
+}
+} // namespace detail
+} // namespace lbfgsb200
+
+std::vector<double> LBFGS(const std::function<double(std::vector<double>)> f,
+                          const std::function<std::vector<double>(std::vector<double>)> grad,
+                          const std::vector<double> x0, const std::string line_search_method,
+                          const int max_iterations, const int m, const double tolerance, bool verbose)
+{
+    return lbfgsb200::detail::run(f, grad, x0, line_search_method, max_iterations, m, tolerance, verbose, false);
+}
+
+std::vector<double> LBFGS_CUDA(const std::function<double(std::vector<double>)> f,
+                               const std::function<std::vector<double>(std::vector<double>)> grad,
+                               const std::vector<double> x0, const std::string line_search_method,
+                               const int max_iterations, const int m, const double tolerance)
+{
+    return lbfgsb200::detail::run(f, grad, x0, line_search_method, max_iterations, m, tolerance, false, true);
+}
+
+std::vector<double> LBFGS_CUDA(const std::function<double(std::vector<double>)> f,
+                               const std::function<std::vector<double>(std::vector<double>)> grad,
+                               const std::vector<double> x0, const int max_iterations, const int m,
+                               const double tolerance)
+{
+    return lbfgsb200::detail::run(f, grad, x0, lbfgsb200::compat_options().cuda_default_line_search, max_iterations,
+                                  m, tolerance, false, true);
+}
+
+#endif // LBFGSB200_COMPAT_IMPLEMENTATION
+#endif // LBFGSB200_COMPAT_HPP

@@ -34,7 +34,7 @@ def build(ref=True):
     """Compile the restatement and, where /root/reference exists, the reference itself."""
     subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
     if ref and os.path.isdir(REFERENCE_ROOT):
-        subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref", "refmain"])
 
 
 class _Params(C.Structure):
