@@ -1,0 +1,429 @@
+// compact.cuh -- the compact ("vector-free" / Gram) form of the L-BFGS direction.
+//
+// The explicit two-loop recursion (seq/lbfgs.cpp:93-143) streams the work vector 2h times
+// because every pass needs a scalar produced by the previous one: (8h-1) vector streams.  The
+// compact form keeps the recursion but runs it on COEFFICIENTS: the direction is a linear
+// combination  d = -sum_j delta_j b_j  of the basis  b = [s_0..s_{h-1}, y_0..y_{h-1}, g], and every
+// inner product the recursion needs (s_i.q, y_i.r with q, r in span(b)) is a delta-weighted sum
+// of entries of the Gram matrix  G = b^T b.  Per iteration only the rows of G that changed are
+// computed -- those of the newest pair (s_c, y_c) and of g -- all DIRECTLY from the vectors (no
+// linearity tricks: y_c = g_new - g_old would cancel badly near convergence):
+//
+//   pass A  k_gram     reads the 2h+1 basis vectors ONCE  -> 3 x (2h+1) inner products
+//   scalar  OP_COMPACT Gram update + the two loops on delta: O(h^2) flops, one thread
+//   pass B  k_combine  reads the 2h+1 basis vectors once, writes d, accumulates g.d
+//
+// => (4h + 3) vector streams instead of (8h - 1); with trials and accept (4h + 2t + 10) V.
+// This is the "batched GEMV over S^T g, Y^T g" variant of the north star: pass A is a skinny
+// (3 x n)(n x (2h+1)) product, HBM-bound at ~0.75 flop/B, so it stays on the FP64 pipe.
+//
+// Pass A stages tiles of ALL basis vectors in shared memory with a two-stage cp.async pipeline,
+// then each warp owns every 8th column and each lane every 32nd element, so the number of
+// accumulators per thread is independent of h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+#include "state.h"
+
+namespace lb {
+
+constexpr int kGramWarps = kThreads / 32;      // 8
+constexpr int kMaxCompactM = 50;               // history sweep of BASELINE config 5 goes to 50
+constexpr int kMaxCols = 2 * kMaxCompactM + 1; // 101
+constexpr int kMaxCW = (kMaxCols + kGramWarps - 1) / kGramWarps; // 13 columns per warp
+constexpr int kGramCtasPerSm = 2;
+constexpr int kCombineCtasPerSm = 3; // 16 x 16-byte loads in flight per thread
+
+// column j of the basis in window order: S positions 0..h-1, Y positions 0..h-1, g
+__device__ __forceinline__ const double *basis_col(const DevState *st, int j, int h)
+{
+    if (j < h) return st->S + (size_t)slot_of(*st, j) * (size_t)st->stride;
+    if (j < 2 * h) return st->Y + (size_t)slot_of(*st, j - h) * (size_t)st->stride;
+    return st->g;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, int src_bytes)
+{
+    // LDGSTS: 16-byte global -> shared copy that bypasses registers; bytes beyond src_bytes are
+    // zero-filled (ragged last tile).
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// pass A.  partials[(j*3 + r) * gridDim.x + cta] = sum over this CTA's tiles of row_r . col_j,
+// rows r = 0: s_newest, 1: y_newest, 2: g.
+//
+// Two-stage cp.async pipeline: while the CTA reduces tile k out of shared memory, the 16-byte
+// async copies of tile k+1 (all 2h+1 vectors x T elements) are already in flight, so a whole
+// tile per CTA -- not a handful of registers per thread -- is outstanding against HBM.
+// Warp w owns columns w, w+8, ...; lane l owns elements l, l+32, ...: CW*3 accumulators per
+// thread, independent of h.  Products are fused (fma): inner products carry no bitwise contract.
+// Rows beyond n: arena rows are 256-byte padded with zeros that are never written, and whole
+// items beyond the padded length are zero-filled by the copy itself.
+template <int CW>
+__global__ void __launch_bounds__(kThreads, kGramCtasPerSm) k_gram(const DevState *__restrict__ st, int T)
+{
+    const int h = st->h;
+    if (st->ctrl.done || st->steepest || h == 0) return;
+    extern __shared__ __align__(128) double tile[]; // [2][J][T]
+    __shared__ const double *cols[kMaxCols];
+    const int J = 2 * h + 1;
+    const long long n = st->n;
+    for (int j = threadIdx.x; j < J; j += kThreads) cols[j] = basis_col(st, j, h);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc[CW][3];
+#pragma unroll
+    for (int c = 0; c < CW; ++c) acc[c][0] = acc[c][1] = acc[c][2] = 0.0;
+    const int r0 = h - 1, r1 = 2 * h - 1, r2 = 2 * h;
+    const int T2 = T >> 1; // double2 items per vector per tile (a power of two)
+    const int log2T2 = 31 - __clz(T2);
+    const long long nvec_pad = (n + 1) >> 1;
+    const long long ntiles = (n + T - 1) / T;
+    const int total = J * T2;
+    const size_t stage_doubles = (size_t)J * T;
+
+    auto issue = [&](long long t, int stage) {
+        const long long base2 = t * T2;
+        double2 *dst = reinterpret_cast<double2 *>(tile + stage * stage_doubles);
+        for (int idx = threadIdx.x; idx < total; idx += kThreads) {
+            const int j = idx >> log2T2, i = idx & (T2 - 1);
+            const bool ok = base2 + i < nvec_pad;
+            const double2 *src = reinterpret_cast<const double2 *>(cols[j]) + (ok ? base2 + i : 0);
+            cp_async16(dst + idx, src, ok ? 16 : 0);
+        }
+        cp_async_commit();
+    };
+
+    long long t = blockIdx.x;
+    int stage = 0;
+    if (t < ntiles) issue(t, 0);
+    for (; t < ntiles; t += gridDim.x, stage ^= 1) {
+        const long long tn = t + gridDim.x;
+        if (tn < ntiles) {
+            issue(tn, stage ^ 1);
+            cp_async_wait<1>(); // everything but the group just committed has landed
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const double *cur = tile + stage * stage_doubles;
+        for (int e = lane; e < T; e += 32) {
+            const double a0 = cur[r0 * T + e], a1 = cur[r1 * T + e], a2 = cur[r2 * T + e];
+#pragma unroll
+            for (int c = 0; c < CW; ++c) {
+                const int j = warp + c * kGramWarps;
+                if (j < J) {
+                    const double v = cur[j * T + e];
+                    acc[c][0] = fma(a0, v, acc[c][0]);
+                    acc[c][1] = fma(a1, v, acc[c][1]);
+                    acc[c][2] = fma(a2, v, acc[c][2]);
+                }
+            }
+        }
+        __syncthreads(); // the next iteration's copies overwrite this stage
+    }
+#pragma unroll
+    for (int c = 0; c < CW; ++c) {
+        const int j = warp + c * kGramWarps;
+        if (j < J) { // warp-uniform
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const double s = warp_sum(acc[c][r]);
+                if (lane == 0) st->partials[(size_t)(j * 3 + r) * gridDim.x + blockIdx.x] = s;
+            }
+        }
+    }
+}
+
+// ---- pass A, TMA variant -------------------------------------------------------------------
+// Same arithmetic, but the tiles are moved by the copy engine: one elected warp issues ONE
+// cp.async.bulk (1-D TMA, SASS UBLKCP) per basis vector and tile, completion is counted in bytes
+// on an mbarrier per stage, and kGramStages stages are kept in flight.  No per-thread copy
+// instructions (the LDGSTS version spends ~40% of its MIO slots issuing copies), shared memory is
+// read back with 128-bit loads, and the warps are split into NG column groups x 8/NG element
+// groups so that each row value is re-read NG times instead of 8.
+constexpr int kGramStages = 4;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned done = 0;
+    for (int spin = 0; !done; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (spin > (1 << 24)) __trap(); // a lost copy must fail the launch, never hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int CW>
+__global__ void __launch_bounds__(kThreads, kGramCtasPerSm)
+k_gram_tma(const DevState *__restrict__ st, int T, int NG)
+{
+    const int h = st->h;
+    if (st->ctrl.done || st->steepest || h == 0) return;
+    extern __shared__ __align__(128) double tile[]; // [kGramStages][J][T]
+    __shared__ const double *cols[kMaxCols];
+    __shared__ __align__(8) unsigned long long full[kGramStages];
+    const int J = 2 * h + 1;
+    const long long npad = st->stride; // rows are zero-padded to a multiple of 32 doubles
+    for (int j = threadIdx.x; j < J; j += kThreads) cols[j] = basis_col(st, j, h);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGramStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int NE = kGramWarps / NG;      // element groups
+    const int cg = warp % NG, eg = warp / NG;
+    double acc[CW][3];
+#pragma unroll
+    for (int c = 0; c < CW; ++c) acc[c][0] = acc[c][1] = acc[c][2] = 0.0;
+    const int r0 = h - 1, r1 = 2 * h - 1, r2 = 2 * h;
+    const long long ntiles = (st->n + T - 1) / T;
+    const size_t stage_doubles = (size_t)J * T;
+    const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    auto issue = [&](long long k) { // warp 0 only
+        const long long t = blockIdx.x + k * (long long)gridDim.x;
+        const long long base = t * T;
+        long long valid = npad - base;
+        if (valid > T) valid = T;
+        const int stage = (int)(k % kGramStages);
+        double *dst = tile + stage * stage_doubles;
+        if (lane == 0) mbar_expect_tx(&full[stage], (unsigned)(J * valid * sizeof(double)));
+        __syncwarp();
+        for (int j = lane; j < J; j += 32)
+            tma_load_1d(dst + (size_t)j * T, cols[j] + base, (unsigned)(valid * sizeof(double)), &full[stage]);
+    };
+
+    if (warp == 0)
+        for (long long k = 0; k < kGramStages - 1 && k < my_tiles; ++k) issue(k);
+    for (long long k = 0; k < my_tiles; ++k) {
+        if (warp == 0 && k + kGramStages - 1 < my_tiles) issue(k + kGramStages - 1);
+        const int stage = (int)(k % kGramStages);
+        mbar_wait(&full[stage], (unsigned)((k / kGramStages) & 1));
+        const long long base = (blockIdx.x + k * (long long)gridDim.x) * T;
+        long long valid = npad - base;
+        if (valid > T) valid = T;
+        const double2 *cur = reinterpret_cast<const double2 *>(tile + stage * stage_doubles);
+        const int T2 = T >> 1, slice2 = T2 / NE; // double2 items per vector / per element group
+        const int e_end = min((eg + 1) * slice2, (int)(valid >> 1));
+        for (int e = eg * slice2 + lane; e < e_end; e += 32) {
+            const double2 a0 = cur[r0 * T2 + e], a1 = cur[r1 * T2 + e], a2 = cur[r2 * T2 + e];
+#pragma unroll
+            for (int c = 0; c < CW; ++c) {
+                const int j = cg + c * NG;
+                if (j < J) {
+                    const double2 v = cur[j * T2 + e];
+                    acc[c][0] = fma(a0.y, v.y, fma(a0.x, v.x, acc[c][0]));
+                    acc[c][1] = fma(a1.y, v.y, fma(a1.x, v.x, acc[c][1]));
+                    acc[c][2] = fma(a2.y, v.y, fma(a2.x, v.x, acc[c][2]));
+                }
+            }
+        }
+        __syncthreads(); // every warp is done with this stage before warp 0 refills it
+    }
+    // cross-warp reduction (fixed order over the NE element groups), one partial per (column,row)
+    double *red = tile; // [NE][J*3], reuses the (now idle) tile storage
+#pragma unroll
+    for (int c = 0; c < CW; ++c) {
+        const int j = cg + c * NG;
+        if (j < J) { // warp-uniform
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const double s = warp_sum(acc[c][r]);
+                if (lane == 0) red[eg * (J * 3) + j * 3 + r] = s;
+            }
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < J * 3; q += kThreads) {
+        double s = 0.0;
+        for (int g = 0; g < NE; ++g) s += red[g * (J * 3) + q];
+        st->partials[(size_t)q * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+// one CTA per (column, row): fixed-order sum of the per-CTA partials -> rows[j*3 + r]
+__global__ void __launch_bounds__(kScalarThreads) k_gram_finalize(DevState *st, int nparts)
+{
+    const int h = st->h;
+    if (st->ctrl.done || st->steepest || h == 0) return;
+    const int q = blockIdx.x;
+    if (q >= 3 * (2 * h + 1)) return;
+    __shared__ double sm[kScalarThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double v = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += kScalarThreads) v += st->partials[(size_t)q * nparts + i];
+    v = warp_sum(v);
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double w = (lane < kScalarThreads / 32) ? sm[lane] : 0.0;
+#pragma unroll
+        for (int o = kScalarThreads / 64; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+        if (lane == 0) st->gram_rows[q] = w;
+    }
+}
+
+// Gram bookkeeping + the two loops of seq/lbfgs.cpp:93-143 on coefficients.  Called by every
+// thread of the scalar kernel's CTA: the Gram update is spread over the threads, the 2h inner
+// products of the recursion are warp-parallel (lane-strided partial sums + the fixed shuffle tree:
+// deterministic), the O(1) updates in between are done by lane 0 of warp 0.
+// rows: the finalised 3 x J inner products of pass A (already summed over ranks on multi-GPU).
+__device__ void compact_recursion(DevState *st, const double *rows)
+{
+    const int h = st->h, J = 2 * h + 1, ns = st->nslots, NB = 2 * ns + 1;
+    const bool seq = st->profile == LBFGSB200_PROFILE_SEQ;
+    double *G = st->gram;
+    __shared__ double delta[kMaxCols];
+    __shared__ int bi[kMaxCols]; // basis index of window column j
+    for (int j = threadIdx.x; j < J; j += kScalarThreads) {
+        bi[j] = j < h ? slot_of(*st, j) : (j < 2 * h ? ns + slot_of(*st, j - h) : 2 * ns);
+        delta[j] = (j == 2 * h) ? 1.0 : 0.0; // q = g
+    }
+    __syncthreads();
+    const int is_new = bi[h - 1], iy_new = bi[2 * h - 1], ig = 2 * ns;
+    const int fresh = st->sg_valid; // the newest pair was committed by the last accept: its rows are new
+    for (int j = threadIdx.x; j < J; j += kScalarThreads) {
+        const int b = bi[j];
+        if (fresh) {
+            G[is_new * NB + b] = rows[j * 3 + 0];
+            G[iy_new * NB + b] = rows[j * 3 + 1];
+        }
+        G[ig * NB + b] = rows[j * 3 + 2];
+    }
+    __syncthreads();
+    // symmetric counterparts (separate phase: (is_new, iy_new) and (iy_new, is_new) are both rows)
+    for (int j = threadIdx.x; j < J; j += kScalarThreads) {
+        const int b = bi[j];
+        if (fresh) {
+            G[b * NB + is_new] = G[is_new * NB + b];
+            G[b * NB + iy_new] = G[iy_new * NB + b];
+        }
+        G[b * NB + ig] = G[ig * NB + b];
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    int bad = 0;
+    // first loop, newest -> oldest (seq/lbfgs.cpp:100-114)
+    for (int p = h - 1; p >= 0; --p) {
+        const int bs = bi[p], by = bi[h + p];
+        const double rho = 1.0 / G[by * NB + bs];
+        if (seq && !isfinite(rho)) bad = 1;
+        double sq = 0.0;
+        for (int j = lane; j < J; j += 32) sq += delta[j] * G[bs * NB + bi[j]];
+        sq = warp_sum(sq);
+        const double a = st->skip[slot_of(*st, p)] ? 0.0 : rho * sq;
+        __syncwarp();
+        if (lane == 0) {
+            st->alpha[p] = a;
+            delta[h + p] = delta[h + p] - a;
+        }
+        __syncwarp();
+    }
+    double gamma = G[is_new * NB + iy_new] / G[iy_new * NB + iy_new]; // :117
+    if (seq) {
+        if (gamma <= 0 || !isfinite(gamma)) bad = 1;
+    } else {
+        const double ys = G[is_new * NB + iy_new], yy = G[iy_new * NB + iy_new];
+        gamma = (yy > 0 && ys > 1e-10) ? ys / yy : 1.0; // par/L-BFGS.cu:246-255
+    }
+    for (int j = lane; j < J; j += 32) delta[j] = delta[j] * gamma; // r = gamma q
+    __syncwarp();
+    // second loop, oldest -> newest (:133-141)
+    for (int p = 0; p < h; ++p) {
+        const int bs = bi[p], by = bi[h + p];
+        const double rho = 1.0 / G[by * NB + bs];
+        double yr = 0.0;
+        for (int j = lane; j < J; j += 32) yr += delta[j] * G[by * NB + bi[j]];
+        yr = warp_sum(yr);
+        const double beta = rho * yr;
+        __syncwarp();
+        if (lane == 0) {
+            const double c = st->skip[slot_of(*st, p)] ? 0.0 : st->alpha[p] - beta;
+            delta[p] = delta[p] + c;
+        }
+        __syncwarp();
+    }
+    for (int j = lane; j < J; j += 32) st->delta[j] = delta[j];
+    if (lane == 0) {
+        st->gamma = gamma;
+        if (bad) { // non-finite rho / bad gamma => d = -g (:103-108, :119-124)
+            st->steepest = 1;
+            st->vec_streams += 2.0;
+        }
+    }
+}
+
+// pass B.  w = d = -(sum_j delta_j b_j), accumulated in window-column order; partial of g.d.
+__global__ void __launch_bounds__(kThreads, kCombineCtasPerSm) k_combine(const DevState *__restrict__ st)
+{
+    const int h = st->h;
+    if (st->ctrl.done || st->steepest || h == 0) return;
+    __shared__ const double *cols[kMaxCols];
+    __shared__ double coef[kMaxCols];
+    const int J = 2 * h + 1;
+    for (int j = threadIdx.x; j < J; j += kThreads) {
+        cols[j] = basis_col(st, j, h);
+        coef[j] = st->delta[j];
+    }
+    __syncthreads();
+    const long long n = st->n;
+    const long long nvec_pad = (n + 1) >> 1;
+    double *__restrict__ w = st->w;
+    double acc_gd = 0.0;
+    constexpr int U = 2; // double2 items per thread per step
+    const long long step = (long long)gridDim.x * kThreads * U;
+    for (long long i0 = ((long long)blockIdx.x * kThreads + threadIdx.x); i0 < nvec_pad; i0 += step) {
+        // items i0 and i0 + gridDim.x*kThreads
+        const long long i1 = i0 + (long long)gridDim.x * kThreads;
+        const bool has1 = i1 < nvec_pad;
+        double2 s0 = make_double2(0.0, 0.0), s1 = s0, g0 = s0, g1 = s0;
+#pragma unroll 8
+        for (int j = 0; j < J; ++j) {
+            const double c = coef[j];
+            const double2 v0 = ld2(cols[j], i0);
+            const double2 v1 = has1 ? ld2(cols[j], i1) : make_double2(0.0, 0.0);
+            s0.x = fma(c, v0.x, s0.x); s0.y = fma(c, v0.y, s0.y);
+            s1.x = fma(c, v1.x, s1.x); s1.y = fma(c, v1.y, s1.y);
+            if (j == J - 1) { g0 = v0; g1 = v1; }
+        }
+        s0.x = -s0.x; s0.y = -s0.y; s1.x = -s1.x; s1.y = -s1.y;
+        st2(w, i0, s0);
+        acc_gd += g0.x * s0.x + g0.y * s0.y;
+        if (has1) {
+            st2(w, i1, s1);
+            acc_gd += g1.x * s1.x + g1.y * s1.y;
+        }
+    }
+    double v[1] = {acc_gd};
+    block_emit<1>(v, st->partials);
+}
+
+} // namespace lb

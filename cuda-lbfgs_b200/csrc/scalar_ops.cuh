@@ -11,12 +11,11 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "compact.cuh"
 #include "kernels.cuh"
 #include "state.h"
 
 namespace lb {
-
-constexpr int kScalarThreads = 256;
 
 // which boundary values a packet carries besides the sums
 enum PackKind : int { PACK_NONE = 0, PACK_X0 = 1, PACK_DIR = 2, PACK_ACCEPT = 3 };
@@ -173,7 +172,7 @@ __device__ void scalar_logic(DevState *st, int op, int p, const double *r)
                 const double ys = st->sy[newest], yy = st->yy[newest];
                 st->gamma = (yy > 0 && ys > 1e-10) ? ys / yy : 1.0;
             }
-            if (!steepest) {
+            if (!steepest && st->direction == LBFGSB200_DIR_TWO_LOOP) {
                 if (st->sg_valid) {
                     const double a = st->skip[newest] ? 0.0 : st->rho[newest] * st->sg; // :109
                     st->alpha[h - 1] = a;
@@ -185,7 +184,10 @@ __device__ void scalar_logic(DevState *st, int op, int p, const double *r)
         }
         st->steepest = steepest;
         // bytes model: two-loop = 8h-1 vector streams, d=-g = 2
-        st->vec_streams += steepest ? 2.0 : (8.0 * h - 1.0) + (st->need_sg ? 2.0 : 0.0);
+        if (st->direction == LBFGSB200_DIR_COMPACT)
+            st->vec_streams += steepest ? 2.0 : (4.0 * h + 3.0); // pass A (2h+1) + pass B (2h+2)
+        else
+            st->vec_streams += steepest ? 2.0 : (8.0 * h - 1.0) + (st->need_sg ? 2.0 : 0.0);
         break;
     }
     case OP_SG: {
@@ -286,6 +288,15 @@ __device__ void scalar_logic(DevState *st, int op, int p, const double *r)
         st->ctrl.k = st->k;
         break;
     }
+    case OP_COMPACT_DIR: {
+        if (st->ctrl.done || st->steepest || st->h == 0) return;
+        st->gd = r[0];
+        if (seq && st->gd >= 0) { // seq/lbfgs.cpp:147-153
+            st->steepest = 1;
+            st->vec_streams += 2.0;
+        }
+        break;
+    }
     default: break;
     }
 }
@@ -317,6 +328,21 @@ k_scalar(DevState *st, int op, int p, int from_comm, int pack_kind, int nparts)
             st->dL = left >= 0 ? rv[left * kPacket + 10] : 0.0;
             st->dR = right < st->nranks ? rv[right * kPacket + 9] : 0.0;
         }
+    }
+    if (op == OP_COMPACT && from_comm) {
+        // rank-ordered sum of the all-gathered pass-A rows (identical bits on every rank)
+        const int cnt = st->gram_count;
+        for (int q = threadIdx.x; q < cnt; q += kScalarThreads) {
+            double v = 0.0;
+            for (int k = 0; k < st->nranks; ++k) v += st->gram_recv[(size_t)k * cnt + q];
+            st->gram_rows[q] = v;
+        }
+        __syncthreads();
+    }
+    if (op == OP_COMPACT) { // CTA-wide: Gram update + coefficient recursion (compact.cuh)
+        if (st->ctrl.done || st->steepest || st->h == 0) return;
+        compact_recursion(st, st->gram_rows);
+        return;
     }
     if (threadIdx.x == 0) scalar_logic(st, op, p, r);
 }

@@ -15,6 +15,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -22,6 +23,7 @@
 
 #include "../../include/lbfgsb200.h"
 #include "comm.h"
+#include "compact.cuh"
 #include "kernels.cuh"
 #include "scalar_ops.cuh"
 #include "state.h"
@@ -86,7 +88,11 @@ struct lbfgsb200_solver {
     int objective = 0;
     size_t n_global = 0, n_local = 0, offset = 0, stride = 0;
     int nslots = 0;
-    int grid = 1, grid_accept = 1;
+    int grid = 1, grid_accept = 1, grid_gram = 1, grid_combine = 1;
+    int gram_T = 512;           // compact form: elements per vector per shared-memory tile
+    int gram_tma = 1, gram_NG = 2; // pass A moved by TMA bulk copies (0: cp.async fallback)
+    size_t gram_smem = 0;
+    double *gram = nullptr;     // compact form: Gram matrix + pass-A rows + delta + all-gather buffer
     lbfgsb200_params_t params;
     lbfgsb200_comm *comm = nullptr;
 
@@ -143,7 +149,7 @@ struct ClassTimer {
 // and halo values are packed, all-gathered (one small NCCL call) and summed in rank order.
 static int scalar_step(lbfgsb200_solver *s, int op, int p, int pack_kind)
 {
-    const int nparts = (op == OP_ACCEPT || op == OP_INIT) ? s->grid_accept : s->grid;
+    const int nparts = (op == OP_ACCEPT || op == OP_INIT) ? s->grid_accept : (op == OP_COMPACT_DIR ? s->grid_combine : s->grid);
     const bool needs_data = (op != OP_ITER_BEGIN && op != OP_LS_INIT);
     if (s->comm && s->comm->nranks > 1 && needs_data) {
         k_pack<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, op, pack_kind, nparts);
@@ -163,7 +169,36 @@ static int launch_direction(lbfgsb200_solver *s)
     const int m = s->params.m;
     const int h_upper = (int)(s->k_host < m ? s->k_host : m);
     LB_TRY(scalar_step(s, OP_ITER_BEGIN, 0, PACK_NONE));
-    if (h_upper > 0) {
+    if (h_upper > 0 && s->params.direction == LBFGSB200_DIR_COMPACT) {
+        // compact form: pass A (Gram rows) -> coefficient recursion -> pass B (combine)
+        const int J = 2 * h_upper + 1;
+        {
+            ClassTimer t(s, KC_PASS);
+            const size_t smem = s->gram_smem;
+            const int cw = (2 * m + 1 + kGramWarps - 1) / kGramWarps;
+            if (s->gram_tma) {
+                k_gram_tma<kMaxCW><<<s->grid_gram, kThreads, smem, s->stream>>>(s->d_st, s->gram_T, s->gram_NG);
+            } else if (cw <= 3) k_gram<3><<<s->grid_gram, kThreads, smem, s->stream>>>(s->d_st, s->gram_T);
+            else if (cw <= 6) k_gram<6><<<s->grid_gram, kThreads, smem, s->stream>>>(s->d_st, s->gram_T);
+            else k_gram<kMaxCW><<<s->grid_gram, kThreads, smem, s->stream>>>(s->d_st, s->gram_T);
+            k_gram_finalize<<<3 * J, kScalarThreads, 0, s->stream>>>(s->d_st, s->grid_gram);
+            s->launches += 2;
+        }
+        const bool multi = s->comm && s->comm->nranks > 1;
+        if (multi) {
+            const int cnt = 3 * (2 * m + 1);
+            double *rows = s->h_snapshot.gram_rows;
+            LB_TRY(comm_allgather(s->comm, rows, s->h_snapshot.gram_recv, cnt, s->stream));
+        }
+        k_scalar<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, OP_COMPACT, 0, multi ? 1 : 0, PACK_NONE, 0);
+        s->launches += 1;
+        {
+            ClassTimer t(s, KC_OTHER);
+            k_combine<<<s->grid_combine, kThreads, 0, s->stream>>>(s->d_st);
+            s->launches += 1;
+        }
+        LB_TRY(scalar_step(s, OP_COMPACT_DIR, 0, PACK_DIR));
+    } else if (h_upper > 0) {
         {
             ClassTimer t(s, KC_OTHER);
             k_dot_sg<<<s->grid, kThreads, 0, s->stream>>>(s->d_st);
@@ -345,6 +380,7 @@ static int check_params(const lbfgsb200_params_t *p)
         set_error("bad flavor/profile/direction");
         return LBFGSB200_ERR_INVALID;
     }
+    if (p->direction == LBFGSB200_DIR_COMPACT && p->m > kMaxCompactM) { set_error("compact direction supports m <= %d", kMaxCompactM); return LBFGSB200_ERR_INVALID; }
     if (p->max_iterations < 0 || p->ls_max_trials < 1) { set_error("bad iteration limits"); return LBFGSB200_ERR_INVALID; }
     return 0;
 }
@@ -377,6 +413,27 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     if (rc < 0) { delete s; return rc; }
     s->grid = pick_grid((long long)s->n_local, s->sms, params->grid_ctas);
     s->grid_accept = pick_grid((long long)s->n_local, s->sms, params->grid_ctas, kCtasPerSmAccept);
+    if (params->direction == LBFGSB200_DIR_COMPACT) {
+        // shared-memory tile of all 2m+1 basis vectors; keep two CTAs per SM resident
+        const int J = 2 * params->m + 1;
+        const char *env = getenv("LBFGSB200_GRAM_TMA");
+        s->gram_tma = env ? atoi(env) : 1;
+        const int stages = s->gram_tma ? kGramStages : 2; // pipeline stages of J x T doubles, two CTAs per SM
+        s->gram_T = 512;
+        while (s->gram_T > 32 && (size_t)stages * J * s->gram_T * sizeof(double) > 100 * 1024) s->gram_T >>= 1;
+        s->gram_smem = (size_t)stages * J * s->gram_T * sizeof(double);
+        // TMA variant: 8 warps = NG column groups x NE element groups.  Each element group should
+        // span >= 32 double2 items (all lanes busy) and no warp may own more than kMaxCW columns.
+        int NE = s->gram_T / 2 / 32;
+        if (NE < 1) NE = 1;
+        if (NE > kGramWarps / 2) NE = kGramWarps / 2;
+        s->gram_NG = kGramWarps / NE;
+        while (s->gram_NG < kGramWarps && (J + s->gram_NG - 1) / s->gram_NG > kMaxCW) s->gram_NG <<= 1;
+        long long tiles = ((long long)s->n_local + s->gram_T - 1) / s->gram_T;
+        const long long full = (long long)s->sms * kGramCtasPerSm;
+        s->grid_combine = pick_grid((long long)s->n_local, s->sms, params->grid_ctas, kCombineCtasPerSm);
+        s->grid_gram = params->grid_ctas > 0 ? params->grid_ctas : (int)(tiles < full ? (tiles < 1 ? 1 : tiles) : full);
+    }
 
     const size_t nvecs = 4 + 2 * (size_t)s->nslots;
     const size_t arena_bytes = nvecs * s->stride * sizeof(double);
@@ -400,8 +457,26 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     CREATE_TRY(cudaEventCreate(&s->ev0));
     CREATE_TRY(cudaEventCreate(&s->ev1));
     CREATE_TRY(cudaMemsetAsync(s->arena, 0, arena_bytes, s->stream));
-    CREATE_TRY(cudaMalloc(&s->partials, sizeof(double) * kMaxQ * (size_t)s->grid));
-    CREATE_TRY(cudaMemsetAsync(s->partials, 0, sizeof(double) * kMaxQ * (size_t)s->grid, s->stream));
+    size_t npart = (size_t)kMaxQ * (size_t)s->grid;
+    if (params->direction == LBFGSB200_DIR_COMPACT) {
+        const size_t need = (size_t)3 * (2 * params->m + 1) * (size_t)s->grid_gram;
+        if (need > npart) npart = need;
+    }
+    CREATE_TRY(cudaMalloc(&s->partials, sizeof(double) * npart));
+    CREATE_TRY(cudaMemsetAsync(s->partials, 0, sizeof(double) * npart, s->stream));
+    size_t gram_nb = 0, gram_cnt = 0;
+    if (params->direction == LBFGSB200_DIR_COMPACT) {
+        gram_nb = (size_t)(2 * s->nslots + 1);
+        gram_cnt = (size_t)3 * (2 * params->m + 1);
+        const size_t total = gram_nb * gram_nb + gram_cnt * (size_t)(nranks + 1) + (size_t)(2 * params->m + 1);
+        CREATE_TRY(cudaMalloc(&s->gram, sizeof(double) * total));
+        CREATE_TRY(cudaMemsetAsync(s->gram, 0, sizeof(double) * total, s->stream));
+        const int smem = (int)s->gram_smem;
+        CREATE_TRY(cudaFuncSetAttribute(k_gram<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CREATE_TRY(cudaFuncSetAttribute(k_gram<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CREATE_TRY(cudaFuncSetAttribute(k_gram<kMaxCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CREATE_TRY(cudaFuncSetAttribute(k_gram_tma<kMaxCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
     CREATE_TRY(cudaMalloc(&s->pkt, sizeof(double) * kPacket * (size_t)(nranks + 1)));
     CREATE_TRY(cudaMemsetAsync(s->pkt, 0, sizeof(double) * kPacket * (size_t)(nranks + 1), s->stream));
     s->trace_rows = trace_rows;
@@ -441,6 +516,13 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     st.recv = s->pkt + kPacket;
     st.trace = s->trace;
     st.trace_rows = (long long)trace_rows;
+    if (s->gram) {
+        st.gram = s->gram;
+        st.gram_rows = s->gram + gram_nb * gram_nb;
+        st.gram_recv = st.gram_rows + gram_cnt;
+        st.delta = st.gram_recv + gram_cnt * (size_t)nranks;
+        st.gram_count = (int)gram_cnt;
+    }
     st.lsp.kind = params->line_search;
     st.lsp.flavor = params->flavor;
     st.lsp.max_trials = params->ls_max_trials;
@@ -466,6 +548,7 @@ void lbfgsb200_destroy(lbfgsb200_solver_t *s)
         for (cudaEvent_t e : s->prof_ev[c]) cudaEventDestroy(e);
     if (s->arena) cudaFree(s->arena);
     if (s->partials) cudaFree(s->partials);
+    if (s->gram) cudaFree(s->gram);
     if (s->pkt) cudaFree(s->pkt);
     if (s->trace) cudaFree(s->trace);
     if (s->d_st) cudaFree(s->d_st);

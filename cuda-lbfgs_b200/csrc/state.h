@@ -24,6 +24,7 @@ constexpr int kTileVec = kThreads * kUnroll; // 1024 double2 = 16 KB per stream 
 constexpr int kMaxQ = 8;             // partial sums one kernel may emit
 constexpr int kPacket = 12;          // doubles per rank in the packed per-step exchange
 constexpr int kMaxRanks = 16;
+constexpr int kScalarThreads = 256;   // the 1-CTA scalar kernel
 
 // scalar-kernel opcodes
 enum Op : int {
@@ -105,8 +106,11 @@ struct DevState {
     double vec_streams;
 
     // ---- compact form (separate allocations; see compact.cuh) ----
-    double *gram;  // Gram matrix of the basis [s slots, y slots, g]
-    double *delta; // direction coefficients on that basis
+    double *gram;      // Gram matrix of the basis [s slots, y slots, g], (2*nslots+1)^2
+    double *gram_rows; // pass-A output: 3 x (2h+1) inner products, window-column order
+    double *gram_recv; // multi-GPU: all-gathered gram_rows, [nranks][gram_count]
+    int gram_count;    // doubles per rank in that exchange: 3 * (2m+1)
+    double *delta;     // direction coefficients by window column
 };
 
 __host__ __device__ inline int slot_of(const DevState &st, int pos)

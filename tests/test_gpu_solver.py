@@ -173,3 +173,33 @@ def test_full_size_properties_n1e8(gpu):
     assert r["bytes_moved"] > 0 and r["device_ms"] > 0
     # f(x0)/n and the first step are statistically the same as the n=1e4 fixture (iid x0)
     assert 400 < f0 / n < 500 and tr[0, 3] > 0
+
+
+@pytest.mark.parametrize("name", ["rosen_1e4_wolfe_par", "rosen_1e4_backtracking_seq", "rosen_4097_interp_m5",
+                                  "rosen_4097_interp_m20", "tridiag_1e4_wolfe_par", "rosen_5_backtracking_seq",
+                                  "quad_1e4_interp_m5"])
+def test_compact_direction_matches_oracle(gpu, oracle, golden, name):
+    """The compact (Gram) form must meet the same bar as the explicit two-loop: iterates within
+    1e-10 of the oracle over the first 20 iterations, same trial counts and history sizes."""
+    case = golden["traces"][name]
+    K = 20 if case["objective"] == "rosenbrock" else 9
+    x0 = oracle.x0(case["n"], case["lo"], case["hi"])
+    xo, io, to = oracle.lbfgs(case["objective"], x0, case["line_search"], case["flavor"], case["m"], K,
+                              case["tolerance"], trace_rows=K)
+    x, info, tr = _solve(gpu, case, K, direction="compact")
+    assert len(tr) == len(to) == io["iterations"]
+    for k in range(len(tr)):
+        assert _close(tr[k][1], to[k][1], TOL_ITERATE), (name, k, "f", tr[k][1], to[k][1])
+        assert tr[k][4] == to[k][4] and tr[k][5] == to[k][5], (name, k)
+    assert relvec(x, xo) <= TOL_ITERATE, (name, relvec(x, xo))
+    assert info["status"] == io["status"]
+
+
+def test_compact_equals_two_loop_large_history(gpu):
+    x0 = gpu.x0_uniform(200001, -2, 2)
+    for m in (3, 33, 50):
+        a, ia, ta = gpu.solve("rosenbrock", x0, "wolfe", "par", trace_rows=60, m=m, max_iterations=60)
+        b, ib, tb = gpu.solve("rosenbrock", x0, "wolfe", "par", trace_rows=60, m=m, max_iterations=60, direction="compact")
+        assert _close(tb[19][1], ta[19][1], 1e-10), (m, tb[19][1], ta[19][1])
+        assert _close(ib["f"], ia["f"], 1e-6), (m, ib["f"], ia["f"])
+        assert ib["bytes_moved"] < ia["bytes_moved"]
