@@ -9,9 +9,11 @@ drawn like the reference mains (mt19937(42)).  Inputs are synthetic; every vecto
 larger than the 126 MB L2, so nothing survives in cache between passes.
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  roofline     -- the two-loop pass kernel (dominant: ~80% of the step), achieved GB/s from
-                  CUDA-event timing of every launch in a separate instrumented run of the same
-                  iterations, against the measured copy peak in MEASURED_PEAKS.json
+  roofline     -- the dominant streaming kernel of the step (plus a table of all of them): achieved
+                  GB/s = algorithmic bytes per launch / CUDA-event time of every launch in a separate
+                  instrumented run of the same iterations, against MEASURED_PEAKS.json:hbm_gbs
+  variants     -- the same measurement with the other direction algorithm (explicit two-loop
+                  recursion vs the compact/Gram form that reads the history once)
   cpu_baseline -- the UNMODIFIED reference (oracle/_ref, sequential outer loop + the CUDA tree's
                   Wolfe search = the hybrid oracle) on one host core, on a bounded sample
   e2e          -- same metric through the host-buffer API: create + H2D x0 + W+K iterations +
@@ -155,7 +157,8 @@ def main():
     ap.add_argument("--n", type=int, default=N_GLOBAL, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--graph", type=int, default=0, help=argparse.SUPPRESS)
-    ap.add_argument("--direction", default="two_loop", help=argparse.SUPPRESS)
+    ap.add_argument("--direction", default="compact", help=argparse.SUPPRESS)
+    ap.add_argument("--single-variant", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -165,6 +168,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_global = args.n
     K, W = args.steps, max(args.warmup, 3)
+    FILL = max(0, M + 2 - W)  # extra untimed iterations before the warm-up so the history is full (h = m)
 
     pkg = load_pkg()
     L = pkg.lib()
@@ -201,95 +205,119 @@ def main():
     out_pinned = pkg.PinnedArray(n_local)
     pkg.x0_uniform(n_local, -2.0, 2.0, seed=42, offset=off, out=x0_pinned.array)
 
-    params = pkg.default_params(FLAVOR, line_search=LINE_SEARCH, m=M, max_iterations=10 ** 9, tolerance=0.0,
-                                use_graph=args.graph, direction=args.direction)
-
-    # ---------------- device-resident timed region ----------------
-    solver = pkg.Solver(OBJECTIVE, n_global, params, comm=comm, trace_rows=W + 2 * K + 8)
-    solver.set_x0(x0_pinned.array)
-    solver.iterate(W)  # warm-up: also fills the history (W >= m => every timed step runs 2m passes)
-    launches0 = solver.result()["kernel_launches"]
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    barrier()
-    t0 = time.perf_counter()
-    solver.iterate(K)
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    if sampler:
-        sampler.stop_flag = True
-    res = solver.result()
-    dev_ms = max_over_ranks(res["device_ms"])
-    wall_ms = max_over_ranks(wall_ms)
-    launches = res["kernel_launches"] - launches0
-    trace = solver.trace()
-    timed_rows = trace[W:W + K]
-    trials = float(np.sum(timed_rows[:, 4])) if len(timed_rows) else 0.0
-    bytes_step = res["bytes_moved"] / K  # local shard, algorithmic
-    value = K / (dev_ms / 1e3)
-
-    # ---------------- per-kernel timing (separate instrumented run of K more steps) ----------------
-    _, classes = solver.iterate_profiled(K)
-    res_p = solver.result()
-    V = 8.0 * n_local
-    h = min(M, W)
-    pass_launches = max(classes["two_loop_pass"]["launches"], 1)
-    pass_bytes = (8 * h - 1) * V / (2 * h)  # average over the 2h passes of a step: (8h-1) V / 2h
-    pass_ms = classes["two_loop_pass"]["ms"] / pass_launches
     peak, peak_src = measured_peak()
-    achieved = pass_bytes / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else 0.0
-    traffic = None
+    V = 8.0 * n_local
+    h = M
+    # algorithmic bytes per launch of each streaming-kernel class
+    class_bytes = {"two_loop_pass": (8 * h - 1) * V / (2 * h), "gram_rows": (2 * h + 1) * V, "combine": (2 * h + 2) * V,
+                   "trial": 2 * V, "accept": 7 * V}
+    class_kernel = {"two_loop_pass": "k_two_loop_pass", "gram_rows": "k_gram", "combine": "k_combine",
+                    "trial": "k_trial", "accept": "k_accept"}
+    traffic_db = {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("k_two_loop_pass", {}).get("dram_bytes_per_launch")
+            traffic_db = json.load(open(tpath))
         except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_two_loop_pass", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": pass_bytes, "avg_launch_ms": pass_ms,
-                "whole_step": {"algorithmic_GB_per_step": bytes_step / 1e9,
-                               "achieved_GBps": bytes_step / (dev_ms / K * 1e-3) / 1e9,
-                               "frac_of_peak": bytes_step / (dev_ms / K * 1e-3) / 1e9 / peak,
-                               "frac_of_8TBps_nominal": bytes_step / (dev_ms / K * 1e-3) / 1e9 / 8000.0},
-                "kernel_classes_ms_per_step": {k: v["ms"] / K for k, v in classes.items()},
-                "instrumented_ms_per_step": res_p["device_ms"] / K}
-    solver.destroy()
+            traffic_db = {}
+
+    def measure(direction, sample_clocks):
+        """Device-resident timed region of K iterations after W warm-up iterations, then a separate
+        instrumented run of K more iterations with a CUDA-event pair around every streaming kernel."""
+        prm = pkg.default_params(FLAVOR, line_search=LINE_SEARCH, m=M, max_iterations=10 ** 9, tolerance=0.0,
+                                 use_graph=args.graph, direction=direction)
+        solver = pkg.Solver(OBJECTIVE, n_global, prm, comm=comm, trace_rows=FILL + W + 2 * K + 8)
+        solver.set_x0(x0_pinned.array)
+        if FILL:
+            solver.iterate(FILL)  # fill the (s, y) history so every timed step uses all m pairs
+        solver.iterate(W)  # warm-up
+        launches0 = solver.result()["kernel_launches"]
+        sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None
+        if sampler:
+            sampler.start()
+        barrier()
+        t0 = time.perf_counter()
+        solver.iterate(K)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        if sampler:
+            sampler.stop_flag = True
+        res = solver.result()
+        dev_ms = max_over_ranks(res["device_ms"])
+        wall_ms = max_over_ranks(wall_ms)
+        launches = res["kernel_launches"] - launches0
+        rows = solver.trace()[FILL + W:FILL + W + K]
+        trials = float(np.sum(rows[:, 4])) if len(rows) else 0.0
+        bytes_step = res["bytes_moved"] / K  # local shard, algorithmic
+        _, classes = solver.iterate_profiled(K)
+        res_p = solver.result()
+        solver.destroy()
+        kernels = {}
+        for name, c in classes.items():
+            if name in class_bytes and c["launches"] > 0 and c["ms"] > 0:
+                ms = c["ms"] / c["launches"]
+                gbs = class_bytes[name] / (ms * 1e-3) / 1e9
+                kernels[class_kernel[name]] = {"launches_per_step": c["launches"] / K, "avg_launch_ms": ms,
+                                               "algorithmic_bytes_per_launch": class_bytes[name], "achieved_GBps": gbs,
+                                               "frac_of_peak": gbs / peak, "ms_per_step": c["ms"] / K,
+                                               "traffic": traffic_db.get(class_kernel[name], {}).get("dram_bytes_per_launch")}
+        dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+        step_gbs = bytes_step / (dev_ms / K * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s",
+                    "frac": kernels[dom]["frac_of_peak"], "traffic": kernels[dom]["traffic"], "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes_per_launch"],
+                    "avg_launch_ms": kernels[dom]["avg_launch_ms"], "kernels": kernels,
+                    "whole_step": {"algorithmic_GB_per_step": bytes_step / 1e9, "achieved_GBps": step_gbs,
+                                   "frac_of_peak": step_gbs / peak, "frac_of_8TBps_nominal": step_gbs / 8000.0},
+                    "instrumented_ms_per_step": res_p["device_ms"] / K}
+        return {"value": K / (dev_ms / 1e3), "ms_per_step": dev_ms / K, "wall_ms_per_step": wall_ms / K,
+                "gpu_launches": int(launches), "trials_per_step": trials / K if K else None, "roofline": roofline,
+                "clocks": sampler.summary() if sampler else None,
+                "final": {"f": res_p["f"], "gnorm": res_p["gnorm"], "iterations": res_p["iterations"]}}
+
+    main_run = measure(args.direction, True)
+    other = "two_loop" if args.direction == "compact" else "compact"
+    other_run = measure(other, False) if not args.single_variant else None
+    params = pkg.default_params(FLAVOR, line_search=LINE_SEARCH, m=M, max_iterations=10 ** 9, tolerance=0.0,
+                                use_graph=args.graph, direction=args.direction)
 
     # ---------------- end to end through the host-buffer API ----------------
     barrier()
     t0 = time.perf_counter()
     s2 = pkg.Solver(OBJECTIVE, n_global, params, comm=comm, trace_rows=0)
     s2.set_x0(x0_pinned.array)      # H2D of x0 from pinned host memory
-    s2.iterate(W + K)
+    s2.iterate(FILL + W + K)
     s2.x(out=out_pinned.array)      # D2H of the result
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     s2.destroy()
-    e2e = {"value": (W + K) / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": 8.0 * n_global / (W + K),
-           "d2h_bytes_per_step": 8.0 * n_global / (W + K),
+    e2e = {"value": (FILL + W + K) / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": 8.0 * n_global / (FILL + W + K),
+           "d2h_bytes_per_step": 8.0 * n_global / (FILL + W + K),
            "what": "create + H2D x0 (pinned) + %d iterations from a cold history + D2H x; wall clock, max over ranks; "
-                   "byte counts are the one-off 8n-byte copies amortised over the iterations of the call" % (W + K)}
+                   "byte counts are the one-off 8n-byte copies amortised over the iterations of the call" % (FILL + W + K)}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = cpu_reference_rate(min(K, 20), 12)
 
     if rank == 0:
-        line = {"metric": "L-BFGS iterations/sec (FP64) at n=1e8, m=10", "value": value, "unit": "iterations/s",
-                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True,
+        line = {"metric": "L-BFGS iterations/sec (FP64) at n=1e8, m=10", "value": main_run["value"], "unit": "iterations/s",
+                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": main_run["ms_per_step"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "Rosenbrock n=%d, m=%d, Wolfe line search (C2=0.7, safeguarded cubic), "
                                        "x0~U(-2,2) mt19937(42), %s direction, %s" %
                                        (n_global, M, args.direction, "CUDA-graph loop" if args.graph else "host-stepped loop"),
-                           "parallelism": "contiguous shards x%d, 1-element halo + packed 12-double all-gather per sync" % world
+                           "parallelism": "contiguous shards x%d, 1-element halo + packed all-gather per sync" % world
                                           if world > 1 else "single GPU",
                            "cache": "inputs larger than L2 (each of the 2m+6 vectors is %.2f GB per GPU)" % (V / 1e9),
-                           "trials_per_step": trials / K if K else None},
-                "wall_ms_per_step": wall_ms / K, "gpu_launches": int(launches), "clocks": sampler.summary() if sampler else None,
-                "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline,
-                "final": {"f": res_p["f"], "gnorm": res_p["gnorm"], "iterations": res_p["iterations"]}}
+                           "trials_per_step": main_run["trials_per_step"],
+                           "history_fill_iterations_before_warmup": FILL},
+                "wall_ms_per_step": main_run["wall_ms_per_step"], "gpu_launches": main_run["gpu_launches"],
+                "clocks": main_run["clocks"], "roofline": main_run["roofline"], "e2e": e2e, "cpu_baseline": cpu_baseline,
+                "final": main_run["final"]}
+        if other_run is not None:
+            line["variants"] = {other: {k: other_run[k] for k in ("value", "ms_per_step", "gpu_launches", "trials_per_step", "final")}}
+            line["variants"][other]["roofline"] = {k: other_run["roofline"][k] for k in ("kernel", "achieved", "frac", "whole_step")}
         print(json.dumps(line))
     if comm is not None:
         comm.destroy()

@@ -276,10 +276,10 @@ class Solver:
         return _check(lib().lbfgsb200_iterate(self.h, iterations), "iterate")
 
     def iterate_profiled(self, iterations):
-        ms = (C.c_double * 4)()
-        cnt = (C.c_int64 * 4)()
+        ms = (C.c_double * 6)()
+        cnt = (C.c_int64 * 6)()
         rc = _check(lib().lbfgsb200_iterate_profiled(self.h, iterations, ms, cnt), "iterate_profiled")
-        names = ("two_loop_pass", "trial", "accept", "other")
+        names = ("two_loop_pass", "trial", "accept", "other", "gram_rows", "combine")
         return rc, {n: dict(ms=ms[i], launches=cnt[i]) for i, n in enumerate(names)}
 
     def x(self, out=None):

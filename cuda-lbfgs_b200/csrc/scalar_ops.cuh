@@ -277,6 +277,7 @@ __device__ void scalar_logic(DevState *st, int op, int p, const double *r)
         st->vec_streams += 7.0; // accept: reads x, d, g ; writes x, g, s, y
         write_trace(st);
         st->k += 1;
+        st->iters_left -= 1;
         if (!seq && sqrt(st->gg) <= st->tolerance) { // par/L-BFGS.cu:353-357
             st->status = LBFGSB200_CONVERGED;
             st->ctrl.done = 1;
@@ -344,7 +345,16 @@ k_scalar(DevState *st, int op, int p, int from_comm, int pack_kind, int nparts)
         compact_recursion(st, st->gram_rows);
         return;
     }
-    if (threadIdx.x == 0) scalar_logic(st, op, p, r);
+    if (threadIdx.x == 0) {
+        scalar_logic(st, op, p, r);
+        if (st->use_graph) {
+            // device-side control flow: the trial loop and the iteration loop are graph WHILE nodes
+            if (op == OP_LS_INIT || op == OP_LS_STEP)
+                cudaGraphSetConditional(st->cond_inner, (st->ctrl.ls_active && !st->ctrl.done) ? 1u : 0u);
+            if (op == OP_ACCEPT || op == OP_ITER_BEGIN || op == OP_LS_STEP)
+                cudaGraphSetConditional(st->cond_outer, (!st->ctrl.done && st->iters_left > 0) ? 1u : 0u);
+        }
+    }
 }
 
 // unit-test surface: finalise nq partial sums into d_out[0..nq)

@@ -102,6 +102,11 @@ struct DevState {
     // boundary values of the neighbours' shards, refreshed once per outer iteration
     double xL, xR, dL, dR, gL, gR;
 
+    // ---- CUDA-graph mode: WHILE-node condition handles set by the scalar kernel ----
+    unsigned long long cond_outer, cond_inner;
+    int use_graph;
+    long long iters_left; // iteration budget of the current iterate() call
+
     // ---- accounting: algorithmic HBM traffic in units of one local vector (8 n bytes) ----
     double vec_streams;
 

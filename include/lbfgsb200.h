@@ -27,6 +27,7 @@ extern "C" {
 #define LBFGSB200_MAX_M 64        /* history pairs (reference default m=10; sweep goes to 50) */
 #define LBFGSB200_TRACE_COLS 8
 #define LBFGSB200_UNIQUE_ID_BYTES 128
+#define LBFGSB200_PROFILE_CLASSES 6
 
 /* line searches selectable by name in the reference: seq/lbfgs.cpp:40-70 */
 typedef enum {
@@ -142,10 +143,12 @@ int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local);
 /* Runs at most `iterations` further steps (or until converged / failed / max_iterations). */
 int lbfgsb200_iterate(lbfgsb200_solver_t *s, int64_t iterations);
 /* As iterate(), but forces the host-stepped path and records a CUDA-event pair around every
- * streaming kernel.  class_ms[0..3] / class_launches[0..3] receive the summed device time and
- * launch count of: 0 two-loop passes, 1 trial evaluations, 2 accept/update, 3 everything else. */
-int lbfgsb200_iterate_profiled(lbfgsb200_solver_t *s, int64_t iterations, double class_ms[4],
-                               int64_t class_launches[4]);
+ * streaming kernel.  class_ms[c] / class_launches[c] receive the summed device time and launch
+ * count of: 0 two-loop passes, 1 trial evaluations, 2 accept/update, 3 other streaming kernels,
+ * 4 compact pass A (Gram rows), 5 compact pass B (combine). */
+int lbfgsb200_iterate_profiled(lbfgsb200_solver_t *s, int64_t iterations,
+                               double class_ms[LBFGSB200_PROFILE_CLASSES],
+                               int64_t class_launches[LBFGSB200_PROFILE_CLASSES]);
 int lbfgsb200_get_x(lbfgsb200_solver_t *s, double *x_local_out); /* host or device pointer */
 int lbfgsb200_get_result(lbfgsb200_solver_t *s, lbfgsb200_result_t *r);
 int64_t lbfgsb200_get_trace(lbfgsb200_solver_t *s, double *rows, size_t max_rows);

@@ -203,3 +203,32 @@ def test_compact_equals_two_loop_large_history(gpu):
         assert _close(tb[19][1], ta[19][1], 1e-10), (m, tb[19][1], ta[19][1])
         assert _close(ib["f"], ia["f"], 1e-6), (m, ib["f"], ia["f"])
         assert ib["bytes_moved"] < ia["bytes_moved"]
+
+
+@pytest.mark.parametrize("direction", ["two_loop", "compact"])
+def test_graph_mode_is_bitwise_identical_to_stepped(gpu, direction):
+    """use_graph=1 replays the SAME kernels in the same order from one CUDA graph whose trial loop
+    and iteration loop are device-controlled WHILE nodes: results must be the same bits."""
+    for objective, n, ls, flavor, K in (("rosenbrock", 10000, "wolfe", "par", 40), ("rosenbrock", 4097, "backtracking", "seq", 25),
+                                        ("tridiag", 10000, "interpolation", "par", 30), ("quadratic", 1000, "wolfe", "par", 10)):
+        lo, hi = (-1000, 1000) if objective == "quadratic" else (-2, 2)
+        x0 = gpu.x0_uniform(n, lo, hi)
+        a, ia, ta = gpu.solve(objective, x0, ls, flavor, trace_rows=K, max_iterations=K, direction=direction)
+        b, ib, tb = gpu.solve(objective, x0, ls, flavor, trace_rows=K, max_iterations=K, direction=direction, use_graph=1)
+        assert np.array_equal(a, b), (objective, direction)
+        assert np.array_equal(ta, tb) and ia["status"] == ib["status"] and ia["iterations"] == ib["iterations"]
+        assert ia["f"] == ib["f"] and ia["trial_evals"] == ib["trial_evals"]
+
+
+def test_graph_mode_resumable_budget(gpu):
+    x0 = gpu.x0_uniform(20000, -2, 2)
+    p = gpu.default_params("par", line_search="wolfe", max_iterations=30, use_graph=1)
+    s = gpu.Solver("rosenbrock", 20000, p, trace_rows=30)
+    s.set_x0(x0)
+    assert s.iterate(7) == 3 and s.result()["iterations"] == 7
+    assert s.iterate(0) == 3 and s.result()["iterations"] == 7
+    assert s.iterate(100) == 1 and s.result()["iterations"] == 30
+    xa = s.x()
+    s.destroy()
+    xb, rb, _ = gpu.solve("rosenbrock", x0, "wolfe", "par", max_iterations=30)
+    assert np.array_equal(xa, xb)
