@@ -57,35 +57,46 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // pass A.  partials[(j*3 + r) * gridDim.x + cta] = sum over this CTA's tiles of row_r . col_j,
 // rows r = 0: s_newest, 1: y_newest, 2: g.
 //
-// Two-stage cp.async pipeline: while the CTA reduces tile k out of shared memory, the 16-byte
-// async copies of tile k+1 (all 2h+1 vectors x T elements) are already in flight, so a whole
-// tile per CTA -- not a handful of registers per thread -- is outstanding against HBM.
+// Multi-stage cp.async pipeline: while the CTA reduces tile k out of shared memory, the 16-byte
+// async copies of tiles k+1 .. k+NS-1 (all 2h+1 vectors x T elements each) are already in
+// flight, so whole tiles per CTA -- not a handful of registers per thread -- are outstanding.
 // Warp w owns columns w, w+8, ...; lane l owns elements l, l+32, ...: CW*3 accumulators per
 // thread, independent of h.  Products are fused (fma): inner products carry no bitwise contract.
 // Rows beyond n: arena rows are 256-byte padded with zeros that are never written, and whole
 // items beyond the padded length are zero-filled by the copy itself.
 template <int CW>
-__global__ void __launch_bounds__(kThreads, kGramCtasPerSm) k_gram(const DevState *__restrict__ st, int T)
+__global__ void __launch_bounds__(kThreads, kGramCtasPerSm)
+k_gram(const DevState *__restrict__ st, int T, int NS, int G)
 {
     const int h = st->h;
     if (st->ctrl.done || st->steepest || h == 0) return;
-    extern __shared__ __align__(128) double tile[]; // [2][J][T]
+    extern __shared__ __align__(128) double tile[]; // [NS][Jt][T]
     __shared__ const double *cols[kMaxCols];
     const int J = 2 * h + 1;
+    // column group of this CTA (blockIdx.y): with G > 1 the basis is split into G groups so that a
+    // tile of one group (+ the three row vectors) still fits a large T; the rows are then re-read
+    // once per group (+3/(J/G) traffic).  G == 1: the rows are simply three of the columns.
+    const int per = (J + G - 1) / G;
+    const int c0 = blockIdx.y * per;
+    const int Jg = min(J, c0 + per) - c0;
+    if (Jg <= 0) return;
+    const int Jt = (G == 1) ? J : Jg + 3;
+    const int rowcol[3] = {h - 1, 2 * h - 1, 2 * h}; // s_newest, y_newest, g
     const long long n = st->n;
-    for (int j = threadIdx.x; j < J; j += kThreads) cols[j] = basis_col(st, j, h);
+    for (int j = threadIdx.x; j < Jt; j += kThreads)
+        cols[j] = basis_col(st, j < Jg ? c0 + j : rowcol[j - Jg], h);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double acc[CW][3];
 #pragma unroll
     for (int c = 0; c < CW; ++c) acc[c][0] = acc[c][1] = acc[c][2] = 0.0;
-    const int r0 = h - 1, r1 = 2 * h - 1, r2 = 2 * h;
+    const int r0 = (G == 1) ? rowcol[0] : Jg, r1 = (G == 1) ? rowcol[1] : Jg + 1, r2 = (G == 1) ? rowcol[2] : Jg + 2;
     const int T2 = T >> 1; // double2 items per vector per tile (a power of two)
     const int log2T2 = 31 - __clz(T2);
     const long long nvec_pad = (n + 1) >> 1;
     const long long ntiles = (n + T - 1) / T;
-    const int total = J * T2;
-    const size_t stage_doubles = (size_t)J * T;
+    const int total = Jt * T2;
+    const size_t stage_doubles = (size_t)Jt * T;
 
     auto issue = [&](long long t, int stage) {
         const long long base2 = t * T2;
@@ -99,16 +110,23 @@ __global__ void __launch_bounds__(kThreads, kGramCtasPerSm) k_gram(const DevStat
         cp_async_commit();
     };
 
-    long long t = blockIdx.x;
+    // NS-stage pipeline: NS-1 tiles are in flight while one is being reduced.  Exactly one group is
+    // committed per prologue slot and per iteration (an empty one when there is nothing left to
+    // fetch), so "all but the newest NS-1 groups have landed" always means "tile k has landed".
+    const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    for (int k = 0; k < NS - 1; ++k) {
+        if (k < my_tiles) issue(blockIdx.x + (long long)k * gridDim.x, k);
+        else cp_async_commit();
+    }
     int stage = 0;
-    if (t < ntiles) issue(t, 0);
-    for (; t < ntiles; t += gridDim.x, stage ^= 1) {
-        const long long tn = t + gridDim.x;
-        if (tn < ntiles) {
-            issue(tn, stage ^ 1);
-            cp_async_wait<1>(); // everything but the group just committed has landed
-        } else {
-            cp_async_wait<0>();
+    for (long long k = 0; k < my_tiles; ++k, stage = (stage + 1 == NS ? 0 : stage + 1)) {
+        const long long kn = k + NS - 1;
+        if (kn < my_tiles) issue(blockIdx.x + kn * gridDim.x, (int)(kn % NS));
+        else cp_async_commit();
+        switch (NS) {
+        case 2: cp_async_wait<1>(); break;
+        case 3: cp_async_wait<2>(); break;
+        default: cp_async_wait<3>(); break;
         }
         __syncthreads();
         const double *cur = tile + stage * stage_doubles;
@@ -117,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, kGramCtasPerSm) k_gram(const DevStat
 #pragma unroll
             for (int c = 0; c < CW; ++c) {
                 const int j = warp + c * kGramWarps;
-                if (j < J) {
+                if (j < Jg) {
                     const double v = cur[j * T + e];
                     acc[c][0] = fma(a0, v, acc[c][0]);
                     acc[c][1] = fma(a1, v, acc[c][1]);
@@ -130,11 +148,11 @@ __global__ void __launch_bounds__(kThreads, kGramCtasPerSm) k_gram(const DevStat
 #pragma unroll
     for (int c = 0; c < CW; ++c) {
         const int j = warp + c * kGramWarps;
-        if (j < J) { // warp-uniform
+        if (j < Jg) { // warp-uniform
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const double s = warp_sum(acc[c][r]);
-                if (lane == 0) st->partials[(size_t)(j * 3 + r) * gridDim.x + blockIdx.x] = s;
+                if (lane == 0) st->partials[(size_t)((c0 + j) * 3 + r) * gridDim.x + blockIdx.x] = s;
             }
         }
     }

@@ -450,10 +450,13 @@ struct EvalOut {
 // One double2 item (elements 2j, 2j+1).  x2/d2/go were loaded by the caller (batched, so the
 // kUnroll requests per stream are all in flight before the first use).  Shuffles are executed
 // by all 32 lanes; inactive lanes (ragged last tile) carry zeros and drop out afterwards.
+// ex/ed: (unguarded path) the x and d of the one element outside the warp's 64-element span that
+// lane 0 (element 2j-1) or lane 31 (element 2j+2) needs, prefetched by the caller in the same
+// batch as the main loads so the stencil never waits for a second, dependent memory round trip.
 template <class OBJ, int MODE, bool GUARD>
 __device__ __forceinline__ void eval_item(const EvalCtx &c, long long j, long long nvec, bool active,
-                                          double2 x2, double2 d2, double2 go, const EvalOut &o,
-                                          double (&acc)[5])
+                                          double2 x2, double2 d2, double2 go, double ex, double ed,
+                                          const EvalOut &o, double (&acc)[5])
 {
     const int lane = threadIdx.x & 31;
     const double xt0 = x2.x + c.alpha * d2.x; // add(x, scalarProduct(alpha, d)): mul, then add
@@ -462,9 +465,15 @@ __device__ __forceinline__ void eval_item(const EvalCtx &c, long long j, long lo
     if (OBJ::kStencil) {
         l = __shfl_up_sync(0xffffffffu, xt1, 1);
         r = __shfl_down_sync(0xffffffffu, xt0, 1);
-        if (!GUARD || active) {
-            if (lane == 0) l = fetch_xt(c, 2 * j - 1);
-            if (lane == 31 || (GUARD && j + 1 >= nvec)) r = fetch_xt(c, 2 * j + 2);
+        if (GUARD) {
+            if (active) {
+                if (lane == 0) l = fetch_xt(c, 2 * j - 1);
+                if (lane == 31 || j + 1 >= nvec) r = fetch_xt(c, 2 * j + 2);
+            }
+        } else {
+            const double et = ex + c.alpha * ed; // same two roundings as every other trial value
+            if (lane == 0) l = (2 * j - 1 < 0) ? c.xtL : et;
+            if (lane == 31) r = (2 * j + 2 >= c.n) ? c.xtR : et;
         }
     }
     if (GUARD && !active) return;
@@ -546,6 +555,24 @@ __device__ __forceinline__ void eval_run(const EvalCtx &c, const EvalOut &o,
 #pragma unroll
             for (int ub = 0; ub < kUnroll; ub += B) {
                 double2 x2[B], d2[B], go[B];
+                double ex[B], ed[B];
+                const int lane = threadIdx.x & 31;
+                if (OBJ::kStencil) {
+                    // branch-free: every lane loads ONE extra element -- lanes 0 / 31 the neighbour
+                    // just outside the warp's span, all other lanes their own first element (a
+                    // sector the 16-byte load below touches anyway)
+#pragma unroll
+                    for (int u = 0; u < B; ++u) {
+                        const long long j = j0 + (ub + u) * kThreads;
+                        long long e = lane == 0 ? 2 * j - 1 : (lane == 31 ? 2 * j + 2 : 2 * j);
+                        e = (e < 0 || e >= c.n) ? 2 * j : e;
+                        ex[u] = c.x[e];
+                        ed[u] = c.d[e];
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < B; ++u) ex[u] = ed[u] = 0.0;
+                }
 #pragma unroll
                 for (int u = 0; u < B; ++u) x2[u] = ld2(c.x, j0 + (ub + u) * kThreads);
 #pragma unroll
@@ -555,7 +582,7 @@ __device__ __forceinline__ void eval_run(const EvalCtx &c, const EvalOut &o,
                     go[u] = (MODE == MODE_ACCEPT) ? ld2(o.gw, j0 + (ub + u) * kThreads) : make_double2(0, 0);
 #pragma unroll
                 for (int u = 0; u < B; ++u)
-                    eval_item<OBJ, MODE, false>(c, j0 + (ub + u) * kThreads, 0, true, x2[u], d2[u], go[u], o, acc);
+                    eval_item<OBJ, MODE, false>(c, j0 + (ub + u) * kThreads, 0, true, x2[u], d2[u], go[u], ex[u], ed[u], o, acc);
             }
         },
         [&](long long j0, long long nvec) {
@@ -569,7 +596,7 @@ __device__ __forceinline__ void eval_run(const EvalCtx &c, const EvalOut &o,
                     d2 = ld2(c.d, j);
                     if (MODE == MODE_ACCEPT) go = ld2(o.gw, j);
                 }
-                eval_item<OBJ, MODE, true>(c, j, nvec, active, x2, d2, go, o, acc);
+                eval_item<OBJ, MODE, true>(c, j, nvec, active, x2, d2, go, 0.0, 0.0, o, acc);
             }
         });
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) eval_tail<OBJ, MODE>(c, o, acc);
@@ -606,22 +633,45 @@ __device__ __forceinline__ EvalCtx make_ctx(const DevState *st, double alpha)
 }
 
 // One line-search trial at alpha = st->ls.alpha: partials f, g.d, g.g.  No global stores.
+// One instantiation per objective (the host knows the objective): no run-time switch, and the
+// register budget is that of one stencil, not the union of all of them.
+template <class OBJ>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_trial(const DevState *__restrict__ st)
 {
     if (st->ctrl.done || !st->ctrl.ls_active) return;
     const EvalCtx c = make_ctx(st, st->ls.alpha);
     const EvalOut o = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    eval_dispatch<MODE_TRIAL>(st->objective, c, o, st->partials);
+    eval_run<OBJ, MODE_TRIAL>(c, o, st->partials);
 }
 
 // Accept the step alpha = st->ls.alpha (init != 0: alpha = 0 on a zeroed d, i.e. evaluate f, g at x0).
+template <class OBJ>
 __global__ void __launch_bounds__(kThreads, kCtasPerSmAccept) k_accept(const DevState *__restrict__ st, int init)
 {
     if (st->ctrl.done) return;
     const EvalCtx c = make_ctx(st, init ? 0.0 : st->ls.alpha);
     const size_t sp = (size_t)spare_slot(*st) * (size_t)st->stride;
     const EvalOut o = {nullptr, st->x_alt, st->g, st->S + sp, st->Y + sp};
-    eval_dispatch<MODE_ACCEPT>(st->objective, c, o, st->partials);
+    eval_run<OBJ, MODE_ACCEPT>(c, o, st->partials);
+}
+
+typedef void (*trial_kernel_t)(const DevState *);
+typedef void (*accept_kernel_t)(const DevState *, int);
+inline trial_kernel_t trial_kernel_for(int objective)
+{
+    switch (objective) {
+    case LBFGSB200_OBJ_QUADRATIC: return k_trial<ObjQuadratic>;
+    case LBFGSB200_OBJ_ROSENBROCK: return k_trial<ObjRosenbrock>;
+    default: return k_trial<ObjTridiag>;
+    }
+}
+inline accept_kernel_t accept_kernel_for(int objective)
+{
+    switch (objective) {
+    case LBFGSB200_OBJ_QUADRATIC: return k_accept<ObjQuadratic>;
+    case LBFGSB200_OBJ_ROSENBROCK: return k_accept<ObjRosenbrock>;
+    default: return k_accept<ObjTridiag>;
+    }
 }
 
 // unit-test surface: explicit pointers, alpha from a device scalar, single shard

@@ -90,11 +90,13 @@ struct lbfgsb200_solver {
     int nslots = 0;
     int grid = 1, grid_accept = 1, grid_gram = 1, grid_combine = 1;
     int gram_T = 512;           // compact form: elements per vector per shared-memory tile
-    int gram_tma = 1, gram_NG = 2; // pass A moved by TMA bulk copies (0: cp.async fallback)
+    int gram_tma = 0, gram_NG = 2, gram_NS = 2, gram_G = 1; // pass A: cp.async pipeline (default) or TMA bulk copies
     size_t gram_smem = 0;
     double *gram = nullptr;     // compact form: Gram matrix + pass-A rows + delta + all-gather buffer
     lbfgsb200_params_t params;
     lbfgsb200_comm *comm = nullptr;
+    trial_kernel_t trial_kernel = nullptr;   // objective-specific instantiations
+    accept_kernel_t accept_kernel = nullptr;
 
     double *arena = nullptr;    // x, x_alt, g, w, S[nslots], Y[nslots]
     double *partials = nullptr; // [kMaxQ][grid]
@@ -180,12 +182,15 @@ static int launch_direction(lbfgsb200_solver *s)
         {
             ClassTimer t(s, KC_GRAM);
             const size_t smem = s->gram_smem;
-            const int cw = (2 * m + 1 + kGramWarps - 1) / kGramWarps;
             if (s->gram_tma) {
                 k_gram_tma<kMaxCW><<<s->grid_gram, kThreads, smem, s->stream>>>(s->d_st, s->gram_T, s->gram_NG);
-            } else if (cw <= 3) k_gram<3><<<s->grid_gram, kThreads, smem, s->stream>>>(s->d_st, s->gram_T);
-            else if (cw <= 6) k_gram<6><<<s->grid_gram, kThreads, smem, s->stream>>>(s->d_st, s->gram_T);
-            else k_gram<kMaxCW><<<s->grid_gram, kThreads, smem, s->stream>>>(s->d_st, s->gram_T);
+            } else {
+                const int G = s->gram_G, per = (2 * m + 1 + G - 1) / G, cwg = (per + kGramWarps - 1) / kGramWarps;
+                const dim3 grid(s->grid_gram, G);
+                if (cwg <= 3) k_gram<3><<<grid, kThreads, smem, s->stream>>>(s->d_st, s->gram_T, s->gram_NS, G);
+                else if (cwg <= 6) k_gram<6><<<grid, kThreads, smem, s->stream>>>(s->d_st, s->gram_T, s->gram_NS, G);
+                else k_gram<kMaxCW><<<grid, kThreads, smem, s->stream>>>(s->d_st, s->gram_T, s->gram_NS, G);
+            }
             k_gram_finalize<<<3 * J, kScalarThreads, 0, s->stream>>>(s->d_st, s->grid_gram);
             s->launches += 2;
         }
@@ -261,7 +266,7 @@ static int run_stepped(lbfgsb200_solver *s, int64_t iterations)
         do {
             {
                 ClassTimer t(s, KC_TRIAL);
-                k_trial<<<s->grid, kThreads, 0, s->stream>>>(s->d_st);
+                s->trial_kernel<<<s->grid, kThreads, 0, s->stream>>>(s->d_st);
                 s->launches += 1;
             }
             LB_TRY(scalar_step(s, OP_LS_STEP, 0, PACK_NONE));
@@ -270,7 +275,7 @@ static int run_stepped(lbfgsb200_solver *s, int64_t iterations)
         if (s->h_ctrl->done) break;
         {
             ClassTimer t(s, KC_ACCEPT);
-            k_accept<<<s->grid_accept, kThreads, 0, s->stream>>>(s->d_st, 0);
+            s->accept_kernel<<<s->grid_accept, kThreads, 0, s->stream>>>(s->d_st, 0);
             s->launches += 1;
         }
         LB_TRY(scalar_step(s, OP_ACCEPT, 0, PACK_ACCEPT));
@@ -352,12 +357,12 @@ static int build_graph(lbfgsb200_solver *s)
     LB_TRY(add_while(iter_body, tail, h_inner, &trial_body));
     std::vector<cudaGraphNode_t> inner_tail;
     LB_TRY(capture_segment(s, trial_body, inner_tail, [&]() {
-        k_trial<<<s->grid, kThreads, 0, s->stream>>>(s->d_st);
+        s->trial_kernel<<<s->grid, kThreads, 0, s->stream>>>(s->d_st);
         return scalar_step(s, OP_LS_STEP, 0, PACK_NONE);
     }));
     const int64_t after_inner = s->launches;
     LB_TRY(capture_segment(s, iter_body, tail, [&]() {
-        k_accept<<<s->grid_accept, kThreads, 0, s->stream>>>(s->d_st, 0);
+        s->accept_kernel<<<s->grid_accept, kThreads, 0, s->stream>>>(s->d_st, 0);
         s->launches += 1;
         return scalar_step(s, OP_ACCEPT, 0, PACK_ACCEPT);
     }));
@@ -390,6 +395,10 @@ static int do_iterate(lbfgsb200_solver *s, int64_t iterations)
     // graph mode: single GPU, not instrumented (NCCL calls and event pairs stay on the stepped path)
     const bool graph = s->params.use_graph && !s->profiling && !(s->comm && s->comm->nranks > 1);
     if (graph && !s->graph_exec) LB_TRY(build_graph(s));
+    if (s->graph_exec) { // cudaGraphSetConditional is only legal inside the graph: gate it per run
+        const int flag = graph ? 1 : 0;
+        CUDA_TRY(cudaMemcpyAsync(&s->d_st->use_graph, &flag, sizeof flag, cudaMemcpyHostToDevice, s->stream));
+    }
     const long long k0 = s->h_snapshot.k, t0 = s->h_snapshot.trial_evals;
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
     int rc = graph ? run_graph(s, iterations) : run_stepped(s, iterations);
@@ -515,6 +524,8 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     if (!s) return LBFGSB200_ERR_NOMEM;
     s->params = *params;
     s->objective = objective;
+    s->trial_kernel = trial_kernel_for(objective);
+    s->accept_kernel = accept_kernel_for(objective);
     s->comm = comm;
     s->n_global = n_global;
     const int rank = comm ? comm->rank : 0, nranks = comm ? comm->nranks : 1;
@@ -534,10 +545,27 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
         // reaches 6.75 TB/s, the 1 KB bulk copies of the TMA variant 4.0 TB/s
         const char *env = getenv("LBFGSB200_GRAM_TMA");
         s->gram_tma = env ? atoi(env) : 0;
-        const int stages = s->gram_tma ? kGramStages : 2; // pipeline stages of J x T doubles, two CTAs per SM
-        s->gram_T = 512;
-        while (s->gram_T > 32 && (size_t)stages * J * s->gram_T * sizeof(double) > 100 * 1024) s->gram_T >>= 1;
-        s->gram_smem = (size_t)stages * J * s->gram_T * sizeof(double);
+        int Jt = J;
+        if (s->gram_tma) {
+            s->gram_NS = kGramStages;
+            s->gram_T = 512;
+            while (s->gram_T > 32 && (size_t)s->gram_NS * J * s->gram_T * sizeof(double) > 100 * 1024) s->gram_T >>= 1;
+        } else {
+            // cp.async pipeline.  Large tiles matter (per-tile barrier/issue overhead): split the basis
+            // into G column groups of <= ~40 columns (+3 row vectors when G > 1), take the largest T
+            // whose double-buffered tile fits ~100 KB (two CTAs per SM), then add stages if room is left.
+            const char *et = getenv("LBFGSB200_GRAM_T"), *es = getenv("LBFGSB200_GRAM_NS"), *eg = getenv("LBFGSB200_GRAM_G");
+            s->gram_G = eg ? atoi(eg) : (J + 40) / 41;
+            const int per = (J + s->gram_G - 1) / s->gram_G;
+            Jt = s->gram_G == 1 ? J : per + 3;
+            s->gram_T = 512;
+            while (s->gram_T > 32 && 2 * (size_t)Jt * s->gram_T * sizeof(double) > 100 * 1024) s->gram_T >>= 1;
+            if (et) s->gram_T = atoi(et);
+            int ns = (int)((100 * 1024) / ((size_t)Jt * s->gram_T * sizeof(double)));
+            s->gram_NS = ns < 2 ? 2 : (ns > 4 ? 4 : ns);
+            if (es) s->gram_NS = atoi(es);
+        }
+        s->gram_smem = (size_t)s->gram_NS * Jt * s->gram_T * sizeof(double);
         // TMA variant: 8 warps = NG column groups x NE element groups.  Each element group should
         // span >= 32 double2 items (all lanes busy) and no warp may own more than kMaxCW columns.
         int NE = s->gram_T / 2 / 32;
@@ -548,7 +576,9 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
         long long tiles = ((long long)s->n_local + s->gram_T - 1) / s->gram_T;
         const long long full = (long long)s->sms * kGramCtasPerSm;
         s->grid_combine = pick_grid((long long)s->n_local, s->sms, params->grid_ctas, kCombineCtasPerSm);
-        s->grid_gram = params->grid_ctas > 0 ? params->grid_ctas : (int)(tiles < full ? (tiles < 1 ? 1 : tiles) : full);
+        long long gx = full / s->gram_G; // the G column groups share the resident-CTA slots
+        if (gx < 1) gx = 1;
+        s->grid_gram = params->grid_ctas > 0 ? params->grid_ctas : (int)(tiles < gx ? (tiles < 1 ? 1 : tiles) : gx);
     }
 
     const size_t nvecs = 4 + 2 * (size_t)s->nslots;
@@ -706,7 +736,7 @@ int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local)
         k_scalar<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, -1, 0, 1, PACK_X0, 0);
         s->launches += 2;
     }
-    k_accept<<<s->grid_accept, kThreads, 0, s->stream>>>(s->d_st, 1);
+    s->accept_kernel<<<s->grid_accept, kThreads, 0, s->stream>>>(s->d_st, 1);
     s->launches += 1;
     LB_TRY(scalar_step(s, OP_INIT, 0, PACK_ACCEPT));
     CUDA_TRY(cudaGetLastError());

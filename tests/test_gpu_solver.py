@@ -232,3 +232,17 @@ def test_graph_mode_resumable_budget(gpu):
     s.destroy()
     xb, rb, _ = gpu.solve("rosenbrock", x0, "wolfe", "par", max_iterations=30)
     assert np.array_equal(xa, xb)
+
+
+def test_graph_and_stepped_runs_can_alternate_on_one_handle(gpu):
+    x0 = gpu.x0_uniform(30000, -2, 2)
+    p = gpu.default_params("par", line_search="wolfe", max_iterations=40, use_graph=1, direction="compact")
+    s = gpu.Solver("rosenbrock", 30000, p, trace_rows=40)
+    s.set_x0(x0)
+    s.iterate(10)              # graph
+    s.iterate_profiled(10)     # host-stepped, instrumented
+    s.iterate(100)             # graph again, to max_iterations
+    xa, ra = s.x(), s.result()
+    s.destroy()
+    xb, rb, _ = gpu.solve("rosenbrock", x0, "wolfe", "par", max_iterations=40, direction="compact")
+    assert ra["iterations"] == 40 and np.array_equal(xa, xb)
