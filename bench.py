@@ -260,7 +260,8 @@ def main():
                 kernels[class_kernel[name]] = {"launches_per_step": c["launches"] / K, "avg_launch_ms": ms,
                                                "algorithmic_bytes_per_launch": class_bytes[name], "achieved_GBps": gbs,
                                                "frac_of_peak": gbs / peak, "ms_per_step": c["ms"] / K,
-                                               "traffic": traffic_db.get(class_kernel[name], {}).get("dram_bytes_per_launch")}
+                                               "traffic": (traffic_db[class_kernel[name]]["dram_over_algorithmic"] * class_bytes[name]
+                                                           if "dram_over_algorithmic" in traffic_db.get(class_kernel[name], {}) else None)}
         dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
         step_gbs = bytes_step / (dev_ms / K * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s",
