@@ -13,9 +13,13 @@
 #include <dlfcn.h>
 #include <nccl.h> // types and enums only; no NCCL symbol is linked
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 namespace lb {
+int setup_mailboxes(lbfgsb200_comm *c);
 void set_error(const char *fmt, ...);
 
 namespace {
@@ -65,6 +69,65 @@ int comm_allgather(lbfgsb200_comm *c, const double *send, double *recv, int coun
 }
 } // namespace lb
 
+namespace lb {
+// Allocate this rank's mailbox, exchange the CUDA IPC handles through NCCL, map every peer's
+// mailbox.  All ranks must agree on the outcome, so the local verdict is all-gathered too.
+int setup_mailboxes(lbfgsb200_comm *c)
+{
+    const int P = c->nranks;
+    // data + flags + one more row of 64-bit words whose first entry is the exchange counter
+    const size_t mail_doubles = (size_t)2 * LBFGSB200_MAIL_RANKS * LBFGSB200_MAIL_WIDTH + (size_t)3 * LBFGSB200_MAIL_RANKS;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    struct Blob {
+        cudaIpcMemHandle_t handle;
+        int device;
+        int ok;
+    };
+    Blob mine;
+    memset(&mine, 0, sizeof mine);
+    mine.device = dev;
+    mine.ok = 1;
+    if (cudaMalloc(&c->mail, mail_doubles * sizeof(double)) != cudaSuccess) mine.ok = 0;
+    if (mine.ok && cudaMemset(c->mail, 0, mail_doubles * sizeof(double)) != cudaSuccess) mine.ok = 0;
+    if (mine.ok && cudaIpcGetMemHandle(&mine.handle, c->mail) != cudaSuccess) mine.ok = 0;
+    cudaGetLastError();
+    char *d_buf = nullptr;
+    if (cudaMalloc(&d_buf, sizeof(Blob) * (size_t)(P + 1)) != cudaSuccess) return -1;
+    std::vector<Blob> all((size_t)P);
+    auto gather = [&]() -> int {
+        if (cudaMemcpy(d_buf, &mine, sizeof mine, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+        if (g_nccl.AllGather(d_buf, d_buf + sizeof(Blob), sizeof(Blob), ncclChar, (ncclComm_t)c->nccl, 0) != ncclSuccess) return -1;
+        if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+        if (cudaMemcpy(all.data(), d_buf + sizeof(Blob), sizeof(Blob) * (size_t)P, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        return 0;
+    };
+    if (gather() != 0) { cudaFree(d_buf); return -1; }
+    std::vector<double *> peers((size_t)P, nullptr);
+    for (int r = 0; r < P && mine.ok; ++r) {
+        if (!all[r].ok) { mine.ok = 0; break; }
+        if (r == c->rank) { peers[r] = c->mail; continue; }
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, dev, all[r].device) != cudaSuccess || !can) { mine.ok = 0; break; }
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { mine.ok = 0; break; }
+        c->opened[r] = p;
+        peers[r] = (double *)p;
+    }
+    cudaGetLastError();
+    // second round: every rank learns whether EVERY rank mapped everything
+    if (gather() != 0) { cudaFree(d_buf); return -1; }
+    cudaFree(d_buf);
+    int all_ok = 1;
+    for (int r = 0; r < P; ++r) all_ok &= all[r].ok;
+    if (!all_ok) return -1;
+    if (cudaMalloc(&c->peers_dev, sizeof(double *) * (size_t)P) != cudaSuccess) return -1;
+    if (cudaMemcpy(c->peers_dev, peers.data(), sizeof(double *) * (size_t)P, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+    c->p2p = 1;
+    return 0;
+}
+} // namespace lb
+
 static_assert(sizeof(ncclUniqueId) <= LBFGSB200_UNIQUE_ID_BYTES, "unique id does not fit");
 
 extern "C" int lbfgsb200_comm_unique_id(char id[LBFGSB200_UNIQUE_ID_BYTES])
@@ -98,16 +161,28 @@ extern "C" int lbfgsb200_comm_create(lbfgsb200_comm_t **out, const char id[LBFGS
         return LBFGSB200_ERR_NCCL;
     }
     lbfgsb200_comm *c = new lbfgsb200_comm;
+    memset(c, 0, sizeof *c);
     c->nccl = comm;
     c->rank = rank;
     c->nranks = nranks;
     *out = c;
+    const char *env = getenv("LBFGSB200_P2P");
+    if (nranks > 1 && nranks <= LBFGSB200_MAIL_RANKS && !(env && atoi(env) == 0)) {
+        if (lb::setup_mailboxes(c) != 0) { // not fatal: keep the NCCL exchange
+            c->p2p = 0;
+        }
+    }
     return 0;
 }
 
 extern "C" void lbfgsb200_comm_destroy(lbfgsb200_comm_t *c)
 {
     if (!c) return;
+    cudaDeviceSynchronize();
+    for (int r = 0; r < LBFGSB200_MAIL_RANKS; ++r)
+        if (c->opened[r]) cudaIpcCloseMemHandle(c->opened[r]);
+    if (c->peers_dev) cudaFree(c->peers_dev);
+    if (c->mail) cudaFree(c->mail);
     if (lb::g_nccl.handle) lb::g_nccl.CommDestroy((ncclComm_t)c->nccl);
     delete c;
 }

@@ -59,14 +59,9 @@ __device__ __forceinline__ int nq_of(int op)
     }
 }
 
-// multi-GPU: local sums + boundary values -> st->send (the host then all-gathers kPacket
-// doubles per rank into st->recv)
-__global__ void __launch_bounds__(kScalarThreads) k_pack(DevState *st, int op, int kind, int nparts)
+// local sums + this shard's boundary values -> one packet of kPacket doubles
+__device__ __forceinline__ void build_packet(const DevState *st, int op, int kind, const double *r, double *s)
 {
-    __shared__ double r[kMaxQ];
-    reduce_partials(st->partials, nparts, nq_of(op), r);
-    if (threadIdx.x != 0) return;
-    double *s = st->send;
     for (int q = 0; q < 5; ++q) s[q] = (q < nq_of(op)) ? r[q] : 0.0;
     const long long n = st->n;
     for (int q = 5; q < kPacket; ++q) s[q] = 0.0;
@@ -84,6 +79,69 @@ __global__ void __launch_bounds__(kScalarThreads) k_pack(DevState *st, int op, i
             s[10] = st->w[n - 1];
         }
     }
+}
+
+// multi-GPU, NCCL exchange: packet -> st->send (the host then all-gathers kPacket doubles per
+// rank into st->recv)
+__global__ void __launch_bounds__(kScalarThreads) k_pack(DevState *st, int op, int kind, int nparts)
+{
+    __shared__ double r[kMaxQ];
+    reduce_partials(st->partials, nparts, nq_of(op), r);
+    if (threadIdx.x != 0) return;
+    build_packet(st, op, kind, r, st->send);
+}
+
+// ---- multi-GPU, peer-to-peer exchange (comm.h) -------------------------------------------------
+__device__ __forceinline__ double *mail_slot(double *base, int parity, int sender)
+{
+    return base + ((size_t)parity * kMailRanks + sender) * kMailWidth;
+}
+__device__ __forceinline__ volatile unsigned long long *mail_flag(double *base, int parity, int sender)
+{
+    return reinterpret_cast<volatile unsigned long long *>(base + (size_t)2 * kMailRanks * kMailWidth) +
+           parity * kMailRanks + sender;
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// All-gather `count` doubles per rank through the mailboxes.  Called by every thread of the
+// 1-CTA scalar kernel.  On return rank r's payload is at mail_slot(st->mail, parity, r) (read it
+// with volatile loads); returns the parity.  Each rank runs on its own GPU, so the bounded spin
+// on the peers' flags is a real rendezvous; a peer that never arrives fails the launch (trap)
+// after 20 s instead of hanging the GPU.
+__device__ int p2p_allgather(DevState *st, const double *src, int count)
+{
+    __shared__ unsigned long long s_seq;
+    // the exchange counter lives in the mailbox (per communicator, not per solver): it stays
+    // monotonic across solver handles that share a communicator and is identical on every rank
+    if (threadIdx.x == 0) {
+        unsigned long long *ctr = const_cast<unsigned long long *>(mail_flag(st->mail, 2, 0));
+        s_seq = ++(*ctr);
+    }
+    __syncthreads();
+    const unsigned long long seq = s_seq;
+    const int par = (int)(seq & 1ull), P = st->nranks, me = st->rank;
+    for (int idx = threadIdx.x; idx < P * count; idx += kScalarThreads) {
+        const int rk = idx / count, i = idx - rk * count;
+        mail_slot(st->peers[rk], par, me)[i] = src[i]; // NVLink store into the peer's HBM
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < P) {
+        *mail_flag(st->peers[threadIdx.x], par, me) = seq;
+        volatile unsigned long long *f = mail_flag(st->mail, par, threadIdx.x);
+        const unsigned long long t0 = global_ns();
+        while (*f < seq) {
+            if (global_ns() - t0 > 20000000000ull) __trap();
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    return par;
 }
 
 __device__ __forceinline__ void write_trace(DevState *st)
@@ -309,29 +367,56 @@ __global__ void __launch_bounds__(kScalarThreads)
 k_scalar(DevState *st, int op, int p, int from_comm, int pack_kind, int nparts)
 {
     __shared__ double r[kMaxQ];
+    __shared__ double pk[kPacket];
     const int nq = nq_of(op);
+    const double *rv = nullptr; // gathered packets, [rank][stride]
+    int rv_stride = kPacket;
     if (!from_comm) {
         reduce_partials(st->partials, nparts, nq, r);
-    } else if (threadIdx.x == 0) {
-        const double *rv = st->recv;
+    } else if (from_comm == 2 && op == OP_COMPACT) {
+        // peer-to-peer: all-gather the pass-A rows and add them in rank order
+        if (!(st->ctrl.done || st->steepest || st->h == 0)) {
+            const int cnt = st->gram_count;
+            const int par = p2p_allgather(st, st->gram_rows, cnt);
+            for (int q = threadIdx.x; q < cnt; q += kScalarThreads) {
+                double v = 0.0;
+                for (int k = 0; k < st->nranks; ++k)
+                    v += const_cast<const volatile double *>(mail_slot(st->mail, par, k))[q];
+                st->gram_rows[q] = v;
+            }
+            __syncthreads();
+        }
+    } else if (from_comm == 2) {
+        // peer-to-peer: pack + exchange inside this kernel
+        reduce_partials(st->partials, nparts, nq, r);
+        if (threadIdx.x == 0) build_packet(st, op, pack_kind, r, pk);
+        __syncthreads();
+        const int par = p2p_allgather(st, pk, kPacket);
+        rv = mail_slot(st->mail, par, 0);
+        rv_stride = kMailWidth;
+    } else {
+        rv = st->recv;
+    }
+    if (rv && threadIdx.x == 0) {
+        const volatile double *v = rv;
         for (int q = 0; q < nq; ++q) {
-            double v = 0.0;
-            for (int k = 0; k < st->nranks; ++k) v += rv[k * kPacket + q];
-            r[q] = v;
+            double t = 0.0;
+            for (int k = 0; k < st->nranks; ++k) t += v[(size_t)k * rv_stride + q];
+            r[q] = t;
         }
         const int left = st->rank - 1, right = st->rank + 1;
         if (pack_kind == PACK_X0 || pack_kind == PACK_ACCEPT) {
-            st->xL = left >= 0 ? rv[left * kPacket + 6] : 0.0;
-            st->xR = right < st->nranks ? rv[right * kPacket + 5] : 0.0;
-            st->gL = left >= 0 ? rv[left * kPacket + 8] : 0.0;
-            st->gR = right < st->nranks ? rv[right * kPacket + 7] : 0.0;
+            st->xL = left >= 0 ? v[(size_t)left * rv_stride + 6] : 0.0;
+            st->xR = right < st->nranks ? v[(size_t)right * rv_stride + 5] : 0.0;
+            st->gL = left >= 0 ? v[(size_t)left * rv_stride + 8] : 0.0;
+            st->gR = right < st->nranks ? v[(size_t)right * rv_stride + 7] : 0.0;
         } else if (pack_kind == PACK_DIR) {
-            st->dL = left >= 0 ? rv[left * kPacket + 10] : 0.0;
-            st->dR = right < st->nranks ? rv[right * kPacket + 9] : 0.0;
+            st->dL = left >= 0 ? v[(size_t)left * rv_stride + 10] : 0.0;
+            st->dR = right < st->nranks ? v[(size_t)right * rv_stride + 9] : 0.0;
         }
     }
-    if (op == OP_COMPACT && from_comm) {
-        // rank-ordered sum of the all-gathered pass-A rows (identical bits on every rank)
+    if (op == OP_COMPACT && from_comm == 1) {
+        // NCCL path: rank-ordered sum of the all-gathered pass-A rows (identical bits on every rank)
         const int cnt = st->gram_count;
         for (int q = threadIdx.x; q < cnt; q += kScalarThreads) {
             double v = 0.0;

@@ -159,10 +159,16 @@ static int scalar_step(lbfgsb200_solver *s, int op, int p, int pack_kind)
     const int nparts = (op == OP_ACCEPT || op == OP_INIT) ? s->grid_accept : (op == OP_COMPACT_DIR ? s->grid_combine : s->grid);
     const bool needs_data = (op != OP_ITER_BEGIN && op != OP_LS_INIT);
     if (s->comm && s->comm->nranks > 1 && needs_data) {
-        k_pack<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, op, pack_kind, nparts);
-        LB_TRY(comm_allgather(s->comm, s->pkt, s->pkt + kPacket, kPacket, s->stream));
-        k_scalar<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, op, p, 1, pack_kind, nparts);
-        s->launches += 2;
+        if (s->comm->p2p) {
+            // pack + NVLink mailbox exchange + scalar logic fused in ONE kernel (scalar_ops.cuh)
+            k_scalar<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, op, p, 2, pack_kind, nparts);
+            s->launches += 1;
+        } else {
+            k_pack<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, op, pack_kind, nparts);
+            LB_TRY(comm_allgather(s->comm, s->pkt, s->pkt + kPacket, kPacket, s->stream));
+            k_scalar<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, op, p, 1, pack_kind, nparts);
+            s->launches += 2;
+        }
     } else {
         k_scalar<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, op, p, 0, PACK_NONE, nparts);
         s->launches += 1;
@@ -195,12 +201,13 @@ static int launch_direction(lbfgsb200_solver *s)
             s->launches += 2;
         }
         const bool multi = s->comm && s->comm->nranks > 1;
-        if (multi) {
+        const bool p2p = multi && s->comm->p2p;
+        if (multi && !p2p) {
             const int cnt = 3 * (2 * m + 1);
             double *rows = s->h_snapshot.gram_rows;
             LB_TRY(comm_allgather(s->comm, rows, s->h_snapshot.gram_recv, cnt, s->stream));
         }
-        k_scalar<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, OP_COMPACT, 0, multi ? 1 : 0, PACK_NONE, 0);
+        k_scalar<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, OP_COMPACT, 0, p2p ? 2 : (multi ? 1 : 0), PACK_NONE, 0);
         s->launches += 1;
         {
             ClassTimer t(s, KC_COMBINE);
@@ -393,7 +400,8 @@ static int do_iterate(lbfgsb200_solver *s, int64_t iterations)
     }
     s->streams_at_start = s->h_snapshot.vec_streams;
     // graph mode: single GPU, not instrumented (NCCL calls and event pairs stay on the stepped path)
-    const bool graph = s->params.use_graph && !s->profiling && !(s->comm && s->comm->nranks > 1);
+    // (multi-GPU: only with the peer-to-peer exchange, whose kernels are ordinary graph nodes)
+    const bool graph = s->params.use_graph && !s->profiling && !(s->comm && s->comm->nranks > 1 && !s->comm->p2p);
     if (graph && !s->graph_exec) LB_TRY(build_graph(s));
     if (s->graph_exec) { // cudaGraphSetConditional is only legal inside the graph: gate it per run
         const int flag = graph ? 1 : 0;
@@ -657,6 +665,11 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     st.S = s->arena + 4 * s->stride;
     st.Y = st.S + (size_t)s->nslots * s->stride;
     st.stride = (long long)s->stride;
+    if (comm && comm->p2p) {
+        st.p2p = 1;
+        st.mail = comm->mail;
+        st.peers = comm->peers_dev;
+    }
     st.partials = s->partials;
     st.send = s->pkt;
     st.recv = s->pkt + kPacket;
@@ -731,10 +744,15 @@ int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local)
     CUDA_TRY(cudaMemsetAsync(st.w, 0, s->stride * sizeof(double), s->stream)); // d = 0
     if (s->comm && s->comm->nranks > 1) {
         // neighbours' boundary x before the first evaluation (one-element halo)
-        k_pack<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, -1, PACK_X0, 0);
-        LB_TRY(comm_allgather(s->comm, s->pkt, s->pkt + kPacket, kPacket, s->stream));
-        k_scalar<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, -1, 0, 1, PACK_X0, 0);
-        s->launches += 2;
+        if (s->comm->p2p) {
+            k_scalar<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, -1, 0, 2, PACK_X0, 0);
+            s->launches += 1;
+        } else {
+            k_pack<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, -1, PACK_X0, 0);
+            LB_TRY(comm_allgather(s->comm, s->pkt, s->pkt + kPacket, kPacket, s->stream));
+            k_scalar<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, -1, 0, 1, PACK_X0, 0);
+            s->launches += 2;
+        }
     }
     s->accept_kernel<<<s->grid_accept, kThreads, 0, s->stream>>>(s->d_st, 1);
     s->launches += 1;

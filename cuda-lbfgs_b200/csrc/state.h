@@ -25,6 +25,8 @@ constexpr int kMaxQ = 8;             // partial sums one kernel may emit
 constexpr int kPacket = 12;          // doubles per rank in the packed per-step exchange
 constexpr int kMaxRanks = 16;
 constexpr int kScalarThreads = 256;   // the 1-CTA scalar kernel
+constexpr int kMailRanks = 16;        // == LBFGSB200_MAIL_RANKS (comm.h)
+constexpr int kMailWidth = 304;       // == LBFGSB200_MAIL_WIDTH: >= kPacket and >= 3*(2*50+1) Gram rows
 
 // scalar-kernel opcodes
 enum Op : int {
@@ -101,6 +103,11 @@ struct DevState {
     // ---- halo (multi-GPU, neighbour-coupled objectives) ----
     // boundary values of the neighbours' shards, refreshed once per outer iteration
     double xL, xR, dL, dR, gL, gR;
+
+    // ---- peer-to-peer mailbox exchange (multi-GPU; see comm.h) ----
+    double *mail;    // this rank's mailbox
+    double **peers;  // [nranks] mailbox pointers of all ranks (own entry == mail)
+    int p2p;
 
     // ---- CUDA-graph mode: WHILE-node condition handles set by the scalar kernel ----
     unsigned long long cond_outer, cond_inner;
