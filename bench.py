@@ -135,6 +135,19 @@ def run_reference_arm(args):
         return 0
     steps = min(args.steps, 30)
     cb = cpu_reference_rate(steps, min(args.warmup, 12))
+    # BASELINE config 1 (the reference's own CPU case) end to end: Rosenbrock n=1e4, m=10, backtracking,
+    # tol 1e-5, unmodified sequential-implementation on one core
+    config1 = None
+    try:
+        import oracle as om
+        if om.Ref.available("seq"):
+            ref = om.Ref("seq")
+            x0 = ref.x0(10000, -2, 2)
+            xr, ir = ref.lbfgs("rosenbrock", x0, "backtracking", 10, 20000, 1e-5)
+            config1 = {"seconds": ir["seconds"], "iterations": ir["g_evals"] - 1, "status": ir["status"],
+                       "iterations_per_s": (ir["g_evals"] - 1) / ir["seconds"], "f": ref.f("rosenbrock", xr)}
+    except Exception as e:  # the headline line must still be printed
+        config1 = {"error": str(e)}
     line = {"impl": "reference", "metric": "L-BFGS iterations/sec (FP64) at n=1e8, m=10", "value": cb["value"],
             "unit": "iterations/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 12),
             "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -142,7 +155,7 @@ def run_reference_arm(args):
             "config": {"workload": "Rosenbrock n=1e8, m=10, Wolfe line search (hybrid CPU reference: "
                                    "sequential-implementation/lbfgs.cpp + parallel-implementation/line_search.cpp), "
                                    "bounded sample scaled linearly in n"},
-            "cpu_baseline": cb,
+            "cpu_baseline": cb, "config1": config1,
             "e2e": {"value": cb["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -158,7 +171,7 @@ def main():
     ap.add_argument("--size", type=int, default=N_GLOBAL, help=argparse.SUPPRESS)  # problem size n
     ap.add_argument("--hist", type=int, default=M, help=argparse.SUPPRESS)         # history size m
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
-    ap.add_argument("--graph", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--graph", type=int, default=1, help=argparse.SUPPRESS)
     ap.add_argument("--direction", default="compact", help=argparse.SUPPRESS)
     ap.add_argument("--single-variant", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()

@@ -353,21 +353,6 @@ k_two_loop_pass(const DevState *__restrict__ st, int loop, int p)
     }
 }
 
-// stand-alone pass for the unit-test surface (lbfgsb200_two_loop): same device code, explicit
-// pointers, coefficient from a device scalar.
-__global__ void __launch_bounds__(kThreads, kCtasPerSm)
-k_pass_explicit(int mode, const double *in, const double *v, const double *dv, double *out,
-                const double *d_coef, const double *d_gs, long long n, double *partials)
-{
-    const double c = *d_coef, gs = *d_gs;
-    switch (mode) {
-    case 0: pass_run<0>(in, v, dv, out, c, 1.0, n, partials); break;
-    case 1: pass_run<1>(in, v, nullptr, out, c, gs, n, partials); break;
-    case 2: pass_run<2>(in, v, dv, out, c, gs, n, partials); break;
-    default: pass_run<3>(in, v, dv, out, c, gs, n, partials); break;
-    }
-}
-
 // ------------------------------------------------------------------
 // objectives: three-point stencils on the trial point xt = x + alpha d
 // ------------------------------------------------------------------

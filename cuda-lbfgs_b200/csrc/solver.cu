@@ -610,7 +610,17 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     CREATE_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaEventCreate(&s->ev0));
     CREATE_TRY(cudaEventCreate(&s->ev1));
-    CREATE_TRY(cudaMemsetAsync(s->arena, 0, arena_bytes, s->stream));
+    // Zero only what must be zero: the work vector w (d = 0 for the x0 evaluation) and the <= 31
+    // pad doubles at the end of every row (the compact kernels read rows up to the padded length).
+    // Everything else is written before it is read; clearing the whole arena would cost a full
+    // HBM pass over (2m+6) vectors on every create().
+    {
+        const size_t pad = s->stride - s->n_local;
+        for (size_t v = 0; v < nvecs; ++v) {
+            if (v == 3) CREATE_TRY(cudaMemsetAsync(s->arena + v * s->stride, 0, s->stride * sizeof(double), s->stream));
+            else if (pad) CREATE_TRY(cudaMemsetAsync(s->arena + v * s->stride + s->n_local, 0, pad * sizeof(double), s->stream));
+        }
+    }
     size_t npart = (size_t)kMaxQ * (size_t)s->grid;
     if (params->direction == LBFGSB200_DIR_COMPACT) {
         const size_t need = (size_t)3 * (2 * params->m + 1) * (size_t)s->grid_gram;

@@ -83,7 +83,6 @@ struct DevState {
     // ---- direction ----
     double alpha[kMaxM]; // per window position (0 = oldest)
     double coef;         // coefficient of the next streaming pass
-    double gscale;       // gamma on the first loop-2 pass / last loop-1 dot, else 1.0
     double gamma;
     double sg;           // s_newest . g (from the accept kernel when the pair was committed)
     int sg_valid;

@@ -246,3 +246,22 @@ def test_graph_and_stepped_runs_can_alternate_on_one_handle(gpu):
     s.destroy()
     xb, rb, _ = gpu.solve("rosenbrock", x0, "wolfe", "par", max_iterations=40, direction="compact")
     assert ra["iterations"] == 40 and np.array_equal(xa, xb)
+
+
+@pytest.mark.parametrize("direction", ["two_loop", "compact"])
+def test_tiny_and_ragged_sizes_match_oracle(gpu, oracle, direction):
+    """n = 1, 2, 3 and sizes around the warp / tile boundaries, odd and even, every objective."""
+    for n in (1, 2, 3, 5, 31, 64, 255, 257, 2049):
+        for objective, ls, flavor in (("rosenbrock", "wolfe", "par"), ("tridiag", "backtracking", "seq"),
+                                      ("quadratic", "interpolation", "par")):
+            lo, hi = (-2, 2)
+            x0 = oracle.x0(n, lo, hi)
+            for m in (1, 4):
+                xo, io, to = oracle.lbfgs(objective, x0, ls, flavor, m, 12, 1e-9, trace_rows=12)
+                x, info, tr = gpu.solve(objective, x0, ls, flavor, trace_rows=12, m=m, max_iterations=12, tolerance=1e-9,
+                                        direction=direction)
+                assert info["status"] == io["status"], (n, objective, m, info["status"], io["status"])
+                assert abs(info["iterations"] - io["iterations"]) <= 1, (n, objective, m)
+                if info["iterations"] == io["iterations"]:
+                    scale = max(np.max(np.abs(xo)), np.max(np.abs(x0)))  # the minimiser of tridiag/quadratic may be 0
+                    assert np.max(np.abs(x - xo)) <= 1e-9 * scale, (n, objective, m, direction)
