@@ -65,7 +65,7 @@ _lib = None
 
 # every symbol include/lbfgsb200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "lbfgsb200_version", "lbfgsb200_strerror", "lbfgsb200_last_error", "lbfgsb200_device_count",
+    "lbfgsb200_create_callback", "lbfgsb200_version", "lbfgsb200_strerror", "lbfgsb200_last_error", "lbfgsb200_device_count",
     "lbfgsb200_params_default", "lbfgsb200_solve", "lbfgsb200_create", "lbfgsb200_set_x0",
     "lbfgsb200_iterate", "lbfgsb200_iterate_profiled", "lbfgsb200_get_x", "lbfgsb200_get_result",
     "lbfgsb200_get_trace", "lbfgsb200_local_size", "lbfgsb200_destroy", "lbfgsb200_shard_range",
@@ -94,6 +94,8 @@ def lib():
                                   C.POINTER(Result), C.c_void_p, C.c_size_t]
     L.lbfgsb200_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_size_t, C.POINTER(Params),
                                    C.c_void_p, C.c_size_t]
+    L.lbfgsb200_create_callback.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Params),
+                                            C.c_size_t]
     L.lbfgsb200_set_x0.argtypes = [C.c_void_p, C.c_void_p]
     L.lbfgsb200_iterate.argtypes = [C.c_void_p, C.c_int64]
     L.lbfgsb200_iterate_profiled.argtypes = [C.c_void_p, C.c_int64, _dp, C.POINTER(C.c_int64)]
@@ -254,12 +256,18 @@ class Comm:
 class Solver:
     """Resumable solver handle (lbfgsb200_create / set_x0 / iterate / get_x)."""
 
-    def __init__(self, objective, n_global, params, comm=None, trace_rows=0):
+    def __init__(self, objective, n_global, params, comm=None, trace_rows=0, callback=None, user=None):
+        """objective: a built-in name, or "callback" with callback = address of a
+        lbfgsb200_fg_device_fn (a C function pointer from a user library) and user = its context."""
         self.h = C.c_void_p()
         self.params = params
         self.trace_rows = trace_rows
-        _check(lib().lbfgsb200_create(C.byref(self.h), OBJ[objective], n_global, C.byref(params),
-                                      comm.h if comm else None, trace_rows), "create")
+        if objective == "callback":
+            _check(lib().lbfgsb200_create_callback(C.byref(self.h), callback, user, n_global, C.byref(params),
+                                                   trace_rows), "create_callback")
+        else:
+            _check(lib().lbfgsb200_create(C.byref(self.h), OBJ[objective], n_global, C.byref(params),
+                                          comm.h if comm else None, trace_rows), "create")
         self.n_local = lib().lbfgsb200_local_size(self.h)
 
     def set_x0(self, x0):

@@ -659,6 +659,59 @@ inline accept_kernel_t accept_kernel_for(int objective)
     }
 }
 
+// Accept step for user (callback) objectives: the gradient at x + alpha d was written to g_new
+// by the callback and f to *d_f; everything else is the same update as k_accept.
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+k_accept_generic(const DevState *__restrict__ st, const double *__restrict__ g_new, const double *__restrict__ d_f,
+                 int init)
+{
+    if (st->ctrl.done) return;
+    const double alpha = init ? 0.0 : st->ls.alpha;
+    const double *__restrict__ x = st->x;
+    const double *__restrict__ d = st->w;
+    double *__restrict__ xw = st->x_alt;
+    double *gw = st->g;
+    const size_t sp = (size_t)spare_slot(*st) * (size_t)st->stride;
+    double *__restrict__ s_out = st->S + sp;
+    double *__restrict__ y_out = st->Y + sp;
+    const long long n = st->n;
+    double acc[5] = {0, 0, 0, 0, 0};
+    auto item = [&](long long j) {
+        const double2 x2 = ld2(x, j), d2 = ld2(d, j), gn = ld2(g_new, j), go = ld2(gw, j);
+        const double xt0 = x2.x + alpha * d2.x, xt1 = x2.y + alpha * d2.y;
+        const double s0 = xt0 - x2.x, s1 = xt1 - x2.y, y0 = gn.x - go.x, y1 = gn.y - go.y;
+        st2(xw, j, make_double2(xt0, xt1));
+        st2(gw, j, gn);
+        st2(s_out, j, make_double2(s0, s1));
+        st2(y_out, j, make_double2(y0, y1));
+        acc[1] += gn.x * gn.x + gn.y * gn.y;
+        acc[2] += s0 * y0 + s1 * y1;
+        acc[3] += y0 * y0 + y1 * y1;
+        acc[4] += s0 * gn.x + s1 * gn.y;
+    };
+    tile_loop(n,
+        [&](long long j0) {
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) item(j0 + u * kThreads);
+        },
+        [&](long long j0, long long nvec) {
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+                if (j0 + u * kThreads < nvec) item(j0 + u * kThreads);
+        });
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        acc[0] += *d_f;
+        if (n & 1) {
+            const long long e = n - 1;
+            const double xt = x[e] + alpha * d[e], gn = g_new[e];
+            const double s = xt - x[e], y = gn - gw[e];
+            xw[e] = xt; gw[e] = gn; s_out[e] = s; y_out[e] = y;
+            acc[1] += gn * gn; acc[2] += s * y; acc[3] += y * y; acc[4] += s * gn;
+        }
+    }
+    block_emit<5>(acc, st->partials);
+}
+
 // unit-test surface: explicit pointers, alpha from a device scalar, single shard
 __global__ void __launch_bounds__(kThreads, kCtasPerSmAccept)
 k_eval_explicit(int mode, int objective, const double *x, const double *d, const double *d_alpha,

@@ -96,6 +96,10 @@ struct lbfgsb200_solver {
     lbfgsb200_params_t params;
     lbfgsb200_comm *comm = nullptr;
     trial_kernel_t trial_kernel = nullptr;   // objective-specific instantiations
+    lbfgsb200_fg_device_fn cb = nullptr;     // user device objective (lbfgsb200_create_callback)
+    void *cb_user = nullptr;
+    double *cb_buf = nullptr;                // g_trial [stride] + {f, g.d, g.g} + a device zero
+    double *x_cur = nullptr;                 // host mirror of DevState::x (the accept step swaps x / x_alt)
     accept_kernel_t accept_kernel = nullptr;
 
     double *arena = nullptr;    // x, x_alt, g, w, S[nslots], Y[nslots]
@@ -154,9 +158,9 @@ struct ClassTimer {
 
 // scalar step: on one GPU the scalar kernel sums the partials itself; on several the local sums
 // and halo values are packed, all-gathered (one small NCCL call) and summed in rank order.
-static int scalar_step(lbfgsb200_solver *s, int op, int p, int pack_kind)
+static int scalar_step(lbfgsb200_solver *s, int op, int p, int pack_kind, int nparts_override = -1)
 {
-    const int nparts = (op == OP_ACCEPT || op == OP_INIT) ? s->grid_accept : (op == OP_COMPACT_DIR ? s->grid_combine : s->grid);
+    const int nparts = nparts_override >= 0 ? nparts_override : (op == OP_ACCEPT || op == OP_INIT) ? s->grid_accept : (op == OP_COMPACT_DIR ? s->grid_combine : s->grid);
     const bool needs_data = (op != OP_ITER_BEGIN && op != OP_LS_INIT);
     if (s->comm && s->comm->nranks > 1 && needs_data) {
         if (s->comm->p2p) {
@@ -392,6 +396,39 @@ static int run_graph(lbfgsb200_solver *s, int64_t iterations)
     return 0;
 }
 
+// host-stepped loop for user (callback) objectives: the callback is launched by the host, so the
+// host has to know after every decision whether another evaluation is wanted
+static int run_stepped_callback(lbfgsb200_solver *s, int64_t iterations)
+{
+    double *g_trial = s->cb_buf, *scal = s->cb_buf + s->stride;
+    const double *d_alpha = &s->d_st->ls.alpha;
+    for (int64_t it = 0; it < iterations; ++it) {
+        LB_TRY(launch_direction(s));
+        LB_TRY(read_ctrl(s));
+        while (s->h_ctrl->ls_active && !s->h_ctrl->done) {
+            if (s->cb(s->x_cur, s->h_snapshot.w, d_alpha, g_trial, s->partials, s->n_local, 0, s->cb_user, s->stream)) {
+                set_error("the objective callback failed");
+                return LBFGSB200_ERR_INVALID;
+            }
+            LB_TRY(scalar_step(s, OP_LS_STEP, 0, PACK_NONE, 1)); // the 3 sums are already final: one "partial" each
+            LB_TRY(read_ctrl(s));
+        }
+        if (s->h_ctrl->done) break;
+        // gradient and f at the accepted step (the last trial may have been at another alpha)
+        if (s->cb(s->x_cur, s->h_snapshot.w, d_alpha, g_trial, scal, s->n_local, 0, s->cb_user, s->stream)) {
+            set_error("the objective callback failed");
+            return LBFGSB200_ERR_INVALID;
+        }
+        k_accept_generic<<<s->grid, kThreads, 0, s->stream>>>(s->d_st, g_trial, scal, 0);
+        s->launches += 1;
+        LB_TRY(scalar_step(s, OP_ACCEPT, 0, PACK_ACCEPT, s->grid));
+        s->x_cur = (s->x_cur == s->arena) ? s->arena + s->stride : s->arena;
+        s->k_host += 1;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 static int do_iterate(lbfgsb200_solver *s, int64_t iterations)
 {
     if (!s->x0_set) {
@@ -401,7 +438,7 @@ static int do_iterate(lbfgsb200_solver *s, int64_t iterations)
     s->streams_at_start = s->h_snapshot.vec_streams;
     // graph mode: single GPU, not instrumented (NCCL calls and event pairs stay on the stepped path)
     // (multi-GPU: only with the peer-to-peer exchange, whose kernels are ordinary graph nodes)
-    const bool graph = s->params.use_graph && !s->profiling && !(s->comm && s->comm->nranks > 1 && !s->comm->p2p);
+    const bool graph = s->params.use_graph && !s->profiling && !s->cb && !(s->comm && s->comm->nranks > 1 && !s->comm->p2p);
     if (graph && !s->graph_exec) LB_TRY(build_graph(s));
     if (s->graph_exec) { // cudaGraphSetConditional is only legal inside the graph: gate it per run
         const int flag = graph ? 1 : 0;
@@ -409,7 +446,7 @@ static int do_iterate(lbfgsb200_solver *s, int64_t iterations)
     }
     const long long k0 = s->h_snapshot.k, t0 = s->h_snapshot.trial_evals;
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
-    int rc = graph ? run_graph(s, iterations) : run_stepped(s, iterations);
+    int rc = graph ? run_graph(s, iterations) : (s->cb ? run_stepped_callback(s, iterations) : run_stepped(s, iterations));
     CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
     if (rc < 0) return rc;
     LB_TRY(snapshot(s));
@@ -522,7 +559,7 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     if (!out) return LBFGSB200_ERR_INVALID;
     *out = nullptr;
     LB_TRY(check_params(params));
-    if (objective < 0 || objective > LBFGSB200_OBJ_TRIDIAG) { set_error("unknown objective %d", objective); return LBFGSB200_ERR_INVALID; }
+    if ((objective < 0 || objective > LBFGSB200_OBJ_TRIDIAG) && objective != LBFGSB200_OBJ_DEVICE_CALLBACK) { set_error("unknown objective %d", objective); return LBFGSB200_ERR_INVALID; }
     if (n_global == 0) { set_error("n must be > 0"); return LBFGSB200_ERR_INVALID; }
     if (lbfgsb200_device_count() < 1) {
         set_error("no usable CUDA device: this library has no CPU fallback");
@@ -718,6 +755,7 @@ void lbfgsb200_destroy(lbfgsb200_solver_t *s)
     if (s->arena) cudaFree(s->arena);
     if (s->partials) cudaFree(s->partials);
     if (s->gram) cudaFree(s->gram);
+    if (s->cb_buf) cudaFree(s->cb_buf);
     if (s->pkt) cudaFree(s->pkt);
     if (s->trace) cudaFree(s->trace);
     if (s->d_st) cudaFree(s->d_st);
@@ -728,6 +766,27 @@ void lbfgsb200_destroy(lbfgsb200_solver_t *s)
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
+}
+
+int lbfgsb200_create_callback(lbfgsb200_solver_t **out, lbfgsb200_fg_device_fn fn, void *user, size_t n,
+                              const lbfgsb200_params_t *params, size_t trace_rows)
+{
+    if (!fn) { set_error("create_callback: fn is NULL"); return LBFGSB200_ERR_INVALID; }
+    int rc = lbfgsb200_create(out, LBFGSB200_OBJ_DEVICE_CALLBACK, n, params, nullptr, trace_rows);
+    if (rc < 0) return rc;
+    lbfgsb200_solver *s = *out;
+    s->cb = fn;
+    s->cb_user = user;
+    cudaError_t e = cudaMalloc(&s->cb_buf, sizeof(double) * (s->stride + 8));
+    if (e == cudaSuccess) e = cudaMemset(s->cb_buf, 0, sizeof(double) * (s->stride + 8));
+    if (e != cudaSuccess) {
+        set_error("create_callback: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        lbfgsb200_destroy(s);
+        *out = nullptr;
+        return LBFGSB200_ERR_NOMEM;
+    }
+    return 0;
 }
 
 size_t lbfgsb200_local_size(const lbfgsb200_solver_t *s) { return s ? s->n_local : 0; }
@@ -764,9 +823,21 @@ int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local)
             s->launches += 2;
         }
     }
-    s->accept_kernel<<<s->grid_accept, kThreads, 0, s->stream>>>(s->d_st, 1);
-    s->launches += 1;
-    LB_TRY(scalar_step(s, OP_INIT, 0, PACK_ACCEPT));
+    if (s->cb) {
+        double *g_trial = s->cb_buf, *scal = s->cb_buf + s->stride, *d_zero = scal + 4;
+        if (s->cb(st.x, st.w, d_zero, g_trial, scal, s->n_local, 0, s->cb_user, s->stream)) {
+            set_error("the objective callback failed");
+            return LBFGSB200_ERR_INVALID;
+        }
+        k_accept_generic<<<s->grid, kThreads, 0, s->stream>>>(s->d_st, g_trial, scal, 1);
+        s->launches += 1;
+        LB_TRY(scalar_step(s, OP_INIT, 0, PACK_ACCEPT, s->grid));
+        s->x_cur = s->arena + s->stride; // OP_INIT swapped x and x_alt
+    } else {
+        s->accept_kernel<<<s->grid_accept, kThreads, 0, s->stream>>>(s->d_st, 1);
+        s->launches += 1;
+        LB_TRY(scalar_step(s, OP_INIT, 0, PACK_ACCEPT));
+    }
     CUDA_TRY(cudaGetLastError());
     LB_TRY(snapshot(s));
     s->k_host = 0;

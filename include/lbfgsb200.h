@@ -57,8 +57,20 @@ typedef enum { LBFGSB200_DIR_TWO_LOOP = 0, LBFGSB200_DIR_COMPACT = 1 } lbfgsb200
 typedef enum {
     LBFGSB200_OBJ_QUADRATIC = 0,
     LBFGSB200_OBJ_ROSENBROCK = 1,
-    LBFGSB200_OBJ_TRIDIAG = 2
+    LBFGSB200_OBJ_TRIDIAG = 2,
+    LBFGSB200_OBJ_DEVICE_CALLBACK = 100 /* lbfgsb200_create_callback */
 } lbfgsb200_obj_t;
+
+/* User objective on the device: the replacement for the reference's host callbacks
+ * `function<double(vector<double>)> f` + `function<vector<double>(vector<double>)> grad`
+ * (seq/lbfgs.h:18-19).  Evaluate at the trial point x + (*d_alpha)*d WITHOUT materialising it:
+ * write grad f there to g_out[0..n) and { f, grad.d, grad.grad } to d_out3[0..3) (all device
+ * memory; d_alpha is a DEVICE scalar, so no host synchronisation is needed).  Enqueue everything
+ * on cuda_stream (a cudaStream_t) and return 0, or non-zero to abort the solve.
+ * lbfgsb200_dot() / lbfgsb200_nrm2() may be used for the reductions. */
+typedef int (*lbfgsb200_fg_device_fn)(const double *x, const double *d, const double *d_alpha,
+                                      double *g_out, double *d_out3, size_t n, size_t global_offset,
+                                      void *user, void *cuda_stream);
 
 typedef enum {
     LBFGSB200_CONVERGED = 0,       /* "Converged!"                 seq/lbfgs.cpp:82  */
@@ -137,6 +149,11 @@ int lbfgsb200_solve(int objective, size_t n, const double *x0_host, double *x_ou
 int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
                      const lbfgsb200_params_t *params, lbfgsb200_comm_t *comm,
                      size_t trace_rows);
+/* Same, with a user device objective instead of a built-in one (single GPU, host-stepped loop;
+ * two-loop or compact direction, all line searches).  fn is called once per line-search trial and
+ * once more at the accepted step. */
+int lbfgsb200_create_callback(lbfgsb200_solver_t **out, lbfgsb200_fg_device_fn fn, void *user,
+                              size_t n, const lbfgsb200_params_t *params, size_t trace_rows);
 /* x0: this rank's shard (n_local doubles), host or device pointer.  Evaluates f(x0), grad f(x0)
  * (seq/lbfgs.cpp:28-30). */
 int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local);
