@@ -65,7 +65,7 @@ _lib = None
 
 # every symbol include/lbfgsb200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "lbfgsb200_create_callback", "lbfgsb200_version", "lbfgsb200_strerror", "lbfgsb200_last_error", "lbfgsb200_device_count",
+    "lbfgsb200_create_callback", "lbfgsb200_checkpoint_save", "lbfgsb200_checkpoint_load", "lbfgsb200_version", "lbfgsb200_strerror", "lbfgsb200_last_error", "lbfgsb200_device_count",
     "lbfgsb200_params_default", "lbfgsb200_solve", "lbfgsb200_create", "lbfgsb200_set_x0",
     "lbfgsb200_iterate", "lbfgsb200_iterate_profiled", "lbfgsb200_get_x", "lbfgsb200_get_result",
     "lbfgsb200_get_trace", "lbfgsb200_local_size", "lbfgsb200_destroy", "lbfgsb200_shard_range",
@@ -97,6 +97,8 @@ def lib():
     L.lbfgsb200_create_callback.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Params),
                                             C.c_size_t]
     L.lbfgsb200_set_x0.argtypes = [C.c_void_p, C.c_void_p]
+    L.lbfgsb200_checkpoint_save.argtypes = [C.c_void_p, C.c_char_p]
+    L.lbfgsb200_checkpoint_load.argtypes = [C.c_void_p, C.c_char_p]
     L.lbfgsb200_iterate.argtypes = [C.c_void_p, C.c_int64]
     L.lbfgsb200_iterate_profiled.argtypes = [C.c_void_p, C.c_int64, _dp, C.POINTER(C.c_int64)]
     L.lbfgsb200_get_x.argtypes = [C.c_void_p, C.c_void_p]
@@ -279,6 +281,12 @@ class Solver:
         else:
             ptr = int(x0)
         _check(lib().lbfgsb200_set_x0(self.h, ptr), "set_x0")
+
+    def save(self, path):
+        _check(lib().lbfgsb200_checkpoint_save(self.h, os.fsencode(path)), "checkpoint_save")
+
+    def load(self, path):
+        _check(lib().lbfgsb200_checkpoint_load(self.h, os.fsencode(path)), "checkpoint_load")
 
     def iterate(self, iterations):
         return _check(lib().lbfgsb200_iterate(self.h, iterations), "iterate")

@@ -791,6 +791,121 @@ int lbfgsb200_create_callback(lbfgsb200_solver_t **out, lbfgsb200_fg_device_fn f
 
 size_t lbfgsb200_local_size(const lbfgsb200_solver_t *s) { return s ? s->n_local : 0; }
 
+// ---- checkpoint / resume ------------------------------------------------------------------------
+struct CkptHeader {
+    char magic[8]; // "LBB200C1"
+    uint64_t n_local, stride, nvecs, gram_doubles, trace_rows, devstate_bytes;
+    int32_t m, objective, direction, profile, rank, nranks, x_is_alt, pad;
+    int64_t k_host;
+};
+
+static size_t gram_doubles_of(const lbfgsb200_solver *s)
+{
+    if (!s->gram) return 0;
+    const size_t nb = (size_t)(2 * s->nslots + 1), cnt = (size_t)3 * (2 * s->params.m + 1);
+    const int nranks = s->comm ? s->comm->nranks : 1;
+    return nb * nb + cnt * (size_t)(nranks + 1) + (size_t)(2 * s->params.m + 1);
+}
+
+static int stream_dev_to_file(FILE *f, const double *dev, size_t count, cudaStream_t st)
+{
+    std::vector<double> buf((size_t)1 << 22); // 32 MB staging
+    for (size_t off = 0; off < count; off += buf.size()) {
+        const size_t c = count - off < buf.size() ? count - off : buf.size();
+        CUDA_TRY(cudaMemcpyAsync(buf.data(), dev + off, c * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (fwrite(buf.data(), sizeof(double), c, f) != c) { set_error("checkpoint: short write"); return LBFGSB200_ERR_INVALID; }
+    }
+    return 0;
+}
+
+static int stream_file_to_dev(FILE *f, double *dev, size_t count, cudaStream_t st)
+{
+    std::vector<double> buf((size_t)1 << 22);
+    for (size_t off = 0; off < count; off += buf.size()) {
+        const size_t c = count - off < buf.size() ? count - off : buf.size();
+        if (fread(buf.data(), sizeof(double), c, f) != c) { set_error("checkpoint: short read"); return LBFGSB200_ERR_INVALID; }
+        CUDA_TRY(cudaMemcpyAsync(dev + off, buf.data(), c * sizeof(double), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+int lbfgsb200_checkpoint_save(lbfgsb200_solver_t *s, const char *path)
+{
+    if (!s || !path || !s->x0_set) { set_error("checkpoint_save: no state to save"); return LBFGSB200_ERR_INVALID; }
+    LB_TRY(snapshot(s));
+    FILE *f = fopen(path, "wb");
+    if (!f) { set_error("checkpoint_save: cannot open %s", path); return LBFGSB200_ERR_INVALID; }
+    CkptHeader h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, "LBB200C1", 8);
+    h.n_local = s->n_local; h.stride = s->stride; h.nvecs = 4 + 2 * (size_t)s->nslots;
+    h.gram_doubles = gram_doubles_of(s); h.trace_rows = s->trace_rows; h.devstate_bytes = sizeof(DevState);
+    h.m = s->params.m; h.objective = s->objective; h.direction = s->params.direction; h.profile = s->params.profile;
+    h.rank = s->comm ? s->comm->rank : 0; h.nranks = s->comm ? s->comm->nranks : 1;
+    h.x_is_alt = (s->h_snapshot.x != s->arena);
+    h.k_host = s->k_host;
+    int rc = 0;
+    if (fwrite(&h, sizeof h, 1, f) != 1 || fwrite(&s->h_snapshot, sizeof(DevState), 1, f) != 1) {
+        set_error("checkpoint_save: short write");
+        rc = LBFGSB200_ERR_INVALID;
+    }
+    if (!rc) rc = stream_dev_to_file(f, s->arena, h.nvecs * h.stride, s->stream);
+    if (!rc && h.gram_doubles) rc = stream_dev_to_file(f, s->gram, h.gram_doubles, s->stream);
+    if (!rc && s->trace_rows) rc = stream_dev_to_file(f, s->trace, s->trace_rows * LBFGSB200_TRACE_COLS, s->stream);
+    fclose(f);
+    return rc;
+}
+
+int lbfgsb200_checkpoint_load(lbfgsb200_solver_t *s, const char *path)
+{
+    if (!s || !path) return LBFGSB200_ERR_INVALID;
+    FILE *f = fopen(path, "rb");
+    if (!f) { set_error("checkpoint_load: cannot open %s", path); return LBFGSB200_ERR_INVALID; }
+    CkptHeader h;
+    DevState st;
+    int rc = 0;
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "LBB200C1", 8) != 0 || h.devstate_bytes != sizeof(DevState) ||
+        fread(&st, sizeof st, 1, f) != 1) {
+        set_error("checkpoint_load: %s is not a checkpoint of this library version", path);
+        rc = LBFGSB200_ERR_INVALID;
+    }
+    const int rank = s->comm ? s->comm->rank : 0, nranks = s->comm ? s->comm->nranks : 1;
+    if (!rc && (h.n_local != s->n_local || h.stride != s->stride || h.m != s->params.m || h.objective != s->objective ||
+                h.direction != s->params.direction || h.profile != s->params.profile || h.rank != rank || h.nranks != nranks ||
+                h.gram_doubles != gram_doubles_of(s) || h.trace_rows != s->trace_rows)) {
+        set_error("checkpoint_load: the checkpoint was written by a solver of a different shape");
+        rc = LBFGSB200_ERR_INVALID;
+    }
+    if (!rc) rc = stream_file_to_dev(f, s->arena, h.nvecs * h.stride, s->stream);
+    if (!rc && h.gram_doubles) rc = stream_file_to_dev(f, s->gram, h.gram_doubles, s->stream);
+    if (!rc && s->trace_rows) rc = stream_file_to_dev(f, s->trace, s->trace_rows * LBFGSB200_TRACE_COLS, s->stream);
+    fclose(f);
+    if (rc) return rc;
+    // scalars come from the file; every pointer and handle from this solver
+    const DevState &cur = s->h_snapshot;
+    st.x = h.x_is_alt ? s->arena + s->stride : s->arena;
+    st.x_alt = h.x_is_alt ? s->arena : s->arena + s->stride;
+    st.g = cur.g; st.w = cur.w; st.S = cur.S; st.Y = cur.Y;
+    st.partials = cur.partials; st.send = cur.send; st.recv = cur.recv; st.trace = cur.trace;
+    st.gram = cur.gram; st.gram_rows = cur.gram_rows; st.gram_recv = cur.gram_recv; st.delta = cur.delta;
+    st.mail = cur.mail; st.peers = cur.peers; st.p2p = cur.p2p;
+    st.cond_outer = cur.cond_outer; st.cond_inner = cur.cond_inner; st.use_graph = cur.use_graph;
+    st.max_iterations = cur.max_iterations; st.tolerance = cur.tolerance; st.lsp = cur.lsp; // the new handle's limits apply
+    if (st.status != LBFGSB200_CONVERGED && st.status != LBFGSB200_LS_FAILED && st.k < st.max_iterations) {
+        st.status = LBFGSB200_RUNNING; // a run that only ran out of iterations may continue
+        st.ctrl.done = 0;
+    }
+    s->h_snapshot = st;
+    CUDA_TRY(cudaMemcpyAsync(s->d_st, &s->h_snapshot, sizeof(DevState), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->k_host = h.k_host;
+    s->x_cur = st.x;
+    s->x0_set = true;
+    return 0;
+}
+
 int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local)
 {
     if (!s || !x0_local) { set_error("set_x0: NULL argument"); return LBFGSB200_ERR_INVALID; }

@@ -170,6 +170,12 @@ int lbfgsb200_get_x(lbfgsb200_solver_t *s, double *x_local_out); /* host or devi
 int lbfgsb200_get_result(lbfgsb200_solver_t *s, lbfgsb200_result_t *r);
 int64_t lbfgsb200_get_trace(lbfgsb200_solver_t *s, double *rows, size_t max_rows);
 size_t lbfgsb200_local_size(const lbfgsb200_solver_t *s);
+/* Checkpoint / resume (new; the reference has none -- SURVEY.md 5): dump this rank's complete solver
+ * state (iterate, gradient, direction, (s, y) ring buffer, device scalars, trace) to a file, and load
+ * it into a handle created with the same n, m, objective, direction and rank layout.  A resumed run
+ * continues bit-for-bit like the uninterrupted one. */
+int lbfgsb200_checkpoint_save(lbfgsb200_solver_t *s, const char *path);
+int lbfgsb200_checkpoint_load(lbfgsb200_solver_t *s, const char *path);
 void lbfgsb200_destroy(lbfgsb200_solver_t *s);
 
 /* Contiguous shard of rank r: every rank owns (n / nranks) rounded down to an even count, the

@@ -265,3 +265,33 @@ def test_tiny_and_ragged_sizes_match_oracle(gpu, oracle, direction):
                 if info["iterations"] == io["iterations"]:
                     scale = max(np.max(np.abs(xo)), np.max(np.abs(x0)))  # the minimiser of tridiag/quadratic may be 0
                     assert np.max(np.abs(x - xo)) <= 1e-9 * scale, (n, objective, m, direction)
+
+
+@pytest.mark.parametrize("direction,graph", [("two_loop", 0), ("compact", 1)])
+def test_checkpoint_resume_is_bitwise(gpu, tmp_path, direction, graph):
+    """Save after 9 steps, resume in a NEW handle, run 14 more: same bits as 23 uninterrupted steps."""
+    n = 50001
+    x0 = gpu.x0_uniform(n, -2, 2)
+    mk = lambda: gpu.Solver("rosenbrock", n, gpu.default_params("par", line_search="wolfe", m=7, max_iterations=23,
+                                                                 direction=direction, use_graph=graph), trace_rows=23)
+    a = mk()
+    a.set_x0(x0)
+    a.iterate(9)
+    path = str(tmp_path / "ckpt.bin")
+    a.save(path)
+    a.iterate(100)
+    xa, ra, ta = a.x(), a.result(), a.trace()
+    a.destroy()
+    b = mk()
+    b.load(path)
+    assert b.result()["iterations"] == 9
+    b.iterate(100)
+    xb, rb, tb = b.x(), b.result(), b.trace()
+    b.destroy()
+    assert ra["iterations"] == rb["iterations"] == 23 and ra["status"] == rb["status"] == 1
+    assert np.array_equal(xa, xb) and np.array_equal(ta, tb) and ra["f"] == rb["f"]
+    # a checkpoint of another shape is refused
+    c = gpu.Solver("rosenbrock", n + 2, gpu.default_params("par", line_search="wolfe", m=7, direction=direction), trace_rows=23)
+    with pytest.raises(gpu.LbfgsError, match="different shape"):
+        c.load(path)
+    c.destroy()
