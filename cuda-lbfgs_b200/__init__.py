@@ -51,7 +51,8 @@ class Params(C.Structure):
 class Result(C.Structure):
     _fields_ = [("status", C.c_int), ("iterations", C.c_int64), ("trial_evals", C.c_int64),
                 ("kernel_launches", C.c_int64), ("f", C.c_double), ("gnorm", C.c_double),
-                ("device_ms", C.c_double), ("bytes_moved", C.c_double)]
+                ("device_ms", C.c_double), ("bytes_moved", C.c_double), ("f0", C.c_double),
+                ("gnorm0", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -185,6 +185,8 @@ __device__ void scalar_logic(DevState *st, int op, int p, const double *r)
         double *t = st->x; st->x = st->x_alt; st->x_alt = t;
         st->f = r[0];
         st->gg = r[1];
+        st->f0 = r[0];
+        st->gg0 = r[1];
         st->k = 0;
         st->h = 0;
         st->base = 0;

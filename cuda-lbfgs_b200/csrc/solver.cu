@@ -1014,6 +1014,8 @@ int lbfgsb200_get_result(lbfgsb200_solver_t *s, lbfgsb200_result_t *r)
     r->gnorm = sqrt(st.gg);
     r->device_ms = s->last_ms;
     r->bytes_moved = s->streams_last * 8.0 * (double)s->n_local;
+    r->f0 = st.f0;
+    r->gnorm0 = sqrt(st.gg0);
     return 0;
 }
 
@@ -1046,12 +1048,19 @@ int lbfgsb200_solve(int objective, size_t n, const double *x0_host, double *x_ou
     if (rc >= 0 && result) lbfgsb200_get_result(s, result);
     if (rc >= 0 && trace) lbfgsb200_get_trace(s, trace, trace_rows);
     if (rc >= 0 && params->verbose) {
-        // the reference's per-iteration line (seq/lbfgs.cpp:77-78), printed from the device trace
+        // the reference's per-iteration line (seq/lbfgs.cpp:77-78: printed at the top of iteration k
+        // with the current f and |grad|), reproduced from the device trace
+        lbfgsb200_result_t r;
+        lbfgsb200_get_result(s, &r);
         std::vector<double> rows((size_t)LBFGSB200_TRACE_COLS * (trace_rows ? trace_rows : 1));
-        int64_t got = trace ? lbfgsb200_get_trace(s, rows.data(), trace_rows) : 0;
-        for (int64_t i = 0; i < got; ++i)
-            printf("Iteration %lld, f = %g, |grad| = %g\n", (long long)rows[i * LBFGSB200_TRACE_COLS] + 1,
-                   rows[i * LBFGSB200_TRACE_COLS + 1], rows[i * LBFGSB200_TRACE_COLS + 2]);
+        const int64_t got = trace ? lbfgsb200_get_trace(s, rows.data(), trace_rows) : 0;
+        const int64_t lines = r.status == LBFGSB200_MAX_ITER ? r.iterations : r.iterations + 1;
+        for (int64_t k = 0; k < lines; ++k) {
+            if (k == 0) printf("Iteration 0, f = %g, |grad| = %g\n", r.f0, r.gnorm0);
+            else if (k - 1 < got)
+                printf("Iteration %lld, f = %g, |grad| = %g\n", (long long)k, rows[(k - 1) * LBFGSB200_TRACE_COLS + 1],
+                       rows[(k - 1) * LBFGSB200_TRACE_COLS + 2]);
+        }
     }
     lbfgsb200_destroy(s);
     return rc;

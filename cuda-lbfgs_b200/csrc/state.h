@@ -91,6 +91,7 @@ struct DevState {
 
     // ---- iterate ----
     double f, gg, gd;
+    double f0, gg0; // at x0
     int k;
     int status;
     Ctrl ctrl;

@@ -115,6 +115,8 @@ typedef struct {
     double gnorm;        /* ||grad f|| at the returned x */
     double device_ms;    /* CUDA-event time of the last iterate()/solve() device region */
     double bytes_moved;  /* algorithmic HBM bytes of that region (bytes model) */
+    double f0;           /* f(x0) and ||grad f(x0)||: the reference's "Iteration 0" line (seq/lbfgs.cpp:77-78) */
+    double gnorm0;
 } lbfgsb200_result_t;
 
 typedef struct lbfgsb200_solver lbfgsb200_solver_t; /* one per GPU / rank */

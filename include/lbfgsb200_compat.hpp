@@ -175,10 +175,18 @@ inline std::vector<double> run(const std::function<double(std::vector<double>)> 
         std::cerr << "lbfgsb200: " << lbfgsb200_strerror(rc) << " (" << lbfgsb200_last_error() << ")" << std::endl;
         throw std::runtime_error(lbfgsb200_last_error());
     }
-    if (verbose)
-        for (int64_t k = 0; k < o.last_result.iterations && (size_t)k < rows; ++k)
-            std::cout << "Iteration " << k + 1 << ", f = " << trace[k * LBFGSB200_TRACE_COLS + 1]
-                      << ", |grad| = " << trace[k * LBFGSB200_TRACE_COLS + 2] << std::endl;
+    if (verbose) {
+        // seq/lbfgs.cpp:76-78: one line at the top of every iteration k with the current f and |grad|
+        const lbfgsb200_result_t &r = o.last_result;
+        const int64_t lines = rc == LBFGSB200_MAX_ITER ? r.iterations : r.iterations + 1;
+        for (int64_t k = 0; k < lines; ++k) {
+            if (k == 0)
+                std::cout << "Iteration 0, f = " << r.f0 << ", |grad| = " << r.gnorm0 << std::endl;
+            else if ((size_t)(k - 1) < rows)
+                std::cout << "Iteration " << k << ", f = " << trace[(k - 1) * LBFGSB200_TRACE_COLS + 1]
+                          << ", |grad| = " << trace[(k - 1) * LBFGSB200_TRACE_COLS + 2] << std::endl;
+        }
+    }
     // the reference's only status channel is stdout (seq/lbfgs.cpp:82, :166, :201)
     if (rc == LBFGSB200_CONVERGED) std::cout << "Converged!" << std::endl;
     else if (rc == LBFGSB200_LS_FAILED) std::cout << "Warning: Line search failed at iteration " << o.last_result.iterations << std::endl;

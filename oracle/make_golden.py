@@ -93,6 +93,20 @@ def main():
     with open(OUT, "w") as fh:
         json.dump(out, fh, indent=1, sort_keys=True)
     print("wrote", os.path.normpath(OUT))
+    # the reference's own verbose stdout (seq/lbfgs.cpp:76-78 + the status line) for two small runs
+    import ctypes as C
+    ref = refs["seq"]
+    ref.L.ref_lbfgs_verbose.restype = C.c_int
+    for name, obj, ls, n, (lo, hi), max_it, m, tol in (("rosen5_backtracking", 1, 0, 5, (-2, 2), 12, 10, 1e-5),
+                                                      ("tridiag64_interpolation", 2, 1, 64, (-2, 2), 20, 10, 1e-5)):
+        x0 = ref.x0(n, lo, hi)
+        buf = C.create_string_buffer(1 << 16)
+        rc = ref.L.ref_lbfgs_verbose(obj, ls, C.c_size_t(n), x0.ctypes.data_as(C.POINTER(C.c_double)), max_it, m,
+                                     C.c_double(tol), buf, C.c_size_t(1 << 16))
+        assert rc > 0, rc
+        path = os.path.join(HERE, "..", "tests", "golden", "verbose_%s.txt" % name)
+        open(path, "w").write(buf.value.decode())
+        print("wrote", os.path.normpath(path))
 
 
 if __name__ == "__main__":

@@ -109,6 +109,28 @@ int ref_lbfgs(int objective, int line_search, size_t n, const double *x0, int ma
     return 1;
 }
 
+// The reference's own stdout for a verbose run (seq/lbfgs.cpp:76-78, :82, :166, :201), copied into
+// out (capacity cap, NUL-terminated).  Used to generate tests/golden/verbose_*.txt.
+int ref_lbfgs_verbose(int objective, int line_search, size_t n, const double *x0, int max_it, int m, double tol,
+                      char *out, size_t cap)
+{
+    Objective o = make_objective(objective, n);
+    vector<double> x(x0, x0 + n);
+    ostringstream captured;
+    streambuf *old = cout.rdbuf(captured.rdbuf());
+    try {
+        LBFGS(o.f, o.g, x, kMethods[line_search & 3], max_it, m, tol, true);
+    } catch (...) {
+        cout.rdbuf(old);
+        return -1;
+    }
+    cout.rdbuf(old);
+    const string s = captured.str();
+    if (s.size() + 1 > cap) return -2;
+    memcpy(out, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+
 double ref_dot(const double *a, const double *b, size_t n)
 {
     return dotProduct(vector<double>(a, a + n), vector<double>(b, b + n));

@@ -23,3 +23,50 @@ def test_unmodified_reference_main_runs_on_the_drop_in(gpu):
     assert "Converged!" in r.stdout and "Function: Quadratic Function" in r.stdout
     m = re.search(r"Optimum value: ([-+0-9.eE]+)", r.stdout)
     assert m and abs(float(m.group(1))) < 1e-15, r.stdout
+
+
+@pytest.fixture(scope="module")
+def verbose_exe(tmp_path_factory, gpu):
+    import subprocess as sp
+    out = str(tmp_path_factory.mktemp("vm") / "verbose_main")
+    libdir = os.path.dirname(gpu.LIB_PATH)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    sp.check_call([cxx, "-std=c++14", "-O1", os.path.join(ROOT, "tests", "verbose_main.cpp"), "-L" + libdir, "-llbfgsb200",
+                   "-Wl,-rpath," + libdir, "-o", out])
+    return out
+
+
+def _numbers(line):
+    return [float(v) for v in re.findall(r"[-+]?\d+\.?\d*(?:[eE][-+]?\d+)?", line)]
+
+
+@pytest.mark.parametrize("case,golden_name", [("rosen5", "verbose_rosen5_backtracking.txt"),
+                                              ("tridiag64", "verbose_tridiag64_interpolation.txt")])
+def test_verbose_output_matches_the_reference_stdout(verbose_exe, case, golden_name):
+    """verbose=true through the shim prints what the reference prints (seq/lbfgs.cpp:76-78, :82, :201):
+    same number of "Iteration k, f = ..., |grad| = ..." lines, same status line, same values to the
+    6 significant digits of operator<< (values at the cancellation floor excepted)."""
+    want = open(os.path.join(ROOT, "tests", "golden", golden_name)).read().strip().splitlines()
+    r = subprocess.run([verbose_exe, case], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = r.stdout.strip().splitlines()
+    assert len(got) == len(want), (got, want)
+    f0 = _numbers(want[0])[1]
+    for g, w in zip(got, want):
+        if not w.startswith("Iteration"):
+            assert g == w  # "Converged!" / "Maximum iterations reached"
+            continue
+        ng, nw = _numbers(g), _numbers(w)
+        assert ng[0] == nw[0]
+        for a, b in zip(ng[1:], nw[1:]):
+            if abs(b) > 1e-9 * f0:
+                assert abs(a - b) <= 2e-5 * abs(b), (g, w)
+        if all(abs(b) > 1e-9 * f0 for b in nw[1:]):
+            assert g == w, (g, w)  # identical text
+
+
+def test_shim_error_behaviour_matches_the_reference(verbose_exe):
+    r = subprocess.run([verbose_exe, "unknown_method"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 4 and "Unknown line search method: newton" in r.stdout  # seq/lbfgs.cpp:69
+    r = subprocess.run([verbose_exe, "unknown_objective"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 3 and "no CPU fallback" in r.stdout
