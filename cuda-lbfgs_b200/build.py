@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "liblbfgsb200.so")
 SOURCES = ["solver.cu", "comm.cpp", "x0gen.cpp"]
-HEADERS = ["state.h", "ls_logic.h", "kernels.cuh", "scalar_ops.cuh", "comm.h", "graph.cuh", "compact.cuh",
+HEADERS = ["state.h", "ls_logic.h", "kernels.cuh", "scalar_ops.cuh", "comm.h", "compact.cuh", "comm.cpp", "x0gen.cpp",
            os.path.join("..", "..", "include", "lbfgsb200.h")]
 
 

@@ -4,7 +4,7 @@
 // kernels (kernels.cuh) and the 1-CTA scalar kernel (scalar_ops.cuh) in the fixed order of one
 // L-BFGS iteration, and -- in host-stepped mode -- reads back a 16-byte control block once per
 // line-search trial to learn whether the device-side state machine wants another trial.  In
-// graph mode (graph.cuh) even that disappears: the iteration loop and the trial loop are CUDA
+// graph mode (build_graph below) even that disappears: the iteration loop and the trial loop are CUDA
 // graph WHILE nodes whose conditions the scalar kernel sets on the device.
 //
 // Replaces: LBFGS() seq/lbfgs.cpp:17-203 ; LBFGS_CUDA() par/L-BFGS.cu:105-382 and the four

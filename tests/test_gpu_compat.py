@@ -70,3 +70,15 @@ def test_shim_error_behaviour_matches_the_reference(verbose_exe):
     assert r.returncode == 4 and "Unknown line search method: newton" in r.stdout  # seq/lbfgs.cpp:69
     r = subprocess.run([verbose_exe, "unknown_objective"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 3 and "no CPU fallback" in r.stdout
+
+
+def test_plain_c_host_uses_the_abi(gpu, tmp_path):
+    """A C99 program (gcc, no C++ / CUDA on the caller's side) drives the library through include/lbfgsb200.h."""
+    exe = str(tmp_path / "c_abi_example")
+    libdir = os.path.dirname(gpu.LIB_PATH)
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", os.path.join(ROOT, "tests", "c_abi_example.c"),
+                           "-L" + libdir, "-llbfgsb200", "-lm", "-Wl,-rpath," + libdir, "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "status=0 (converged) iterations=2" in r.stdout and "Unknown line search method" in r.stdout

@@ -149,3 +149,12 @@ def test_no_cpu_fallback(pkg):
         pytest.skip("a CUDA device is present")
     with pytest.raises(pkg.LbfgsError, match="no CPU fallback"):
         pkg.solve("quadratic", np.zeros(16))
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/lbfgsb200.h must be consumable by a C compiler (the drop-in boundary is a C ABI)."""
+    src = tmp_path / "t.c"
+    src.write_text('#include "%s"\nint main(void) { lbfgsb200_params_t p; (void)p; return LBFGSB200_VERSION == 100 ? 0 : 1; }\n'
+                   % os.path.join(ROOT, "include", "lbfgsb200.h"))
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", str(src)])
