@@ -159,12 +159,12 @@ k_gram(const DevState *__restrict__ st, int T, int NS, int G)
 }
 
 // ---- pass A, TMA variant -------------------------------------------------------------------
-// Same arithmetic, but the tiles are moved by the copy engine: one elected warp issues ONE
+// Same arithmetic, but the tiles are moved by the copy engine: a producer warp issues ONE
 // cp.async.bulk (1-D TMA, SASS UBLKCP) per basis vector and tile, completion is counted in bytes
 // on an mbarrier per stage, and kGramStages stages are kept in flight.  No per-thread copy
 // instructions (the LDGSTS version spends ~40% of its MIO slots issuing copies), shared memory is
-// read back with 128-bit loads, and the warps are split into NG column groups x 8/NG element
-// groups so that each row value is re-read NG times instead of 8.
+// read back with 128-bit loads, and the consumer warps are split into NG column groups x 16/NG
+// element groups so that each row value is re-read NG times.
 constexpr int kGramStages = 4;
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -197,89 +197,111 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
                  : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Warp-specialised pass A: ONE CTA per SM owning ~200 KB of shared memory.
+//   warp 0            producer: per tile, one cp.async.bulk (1-D TMA) per basis vector into the next
+//                     free stage; completion is counted in bytes on full[stage]
+//   warps 1..16       consumers: wait on full[stage], reduce their (column group, element group) share
+//                     of the tile with 128-bit shared-memory loads, then release the stage by arriving
+//                     on empty[stage] -- no CTA-wide barrier inside the loop
+// kGramStages-1 whole tiles (all 2h+1 vectors) per SM are in flight while one is being reduced.
+constexpr int kWsConsumerWarps = 16;
+constexpr int kWsThreads = 32 * (kWsConsumerWarps + 1);
+
 template <int CW>
-__global__ void __launch_bounds__(kThreads, kGramCtasPerSm)
-k_gram_tma(const DevState *__restrict__ st, int T, int NG)
+__global__ void __launch_bounds__(kWsThreads, 1) k_gram_tma(const DevState *__restrict__ st, int T, int NG)
 {
     const int h = st->h;
     if (st->ctrl.done || st->steepest || h == 0) return;
     extern __shared__ __align__(128) double tile[]; // [kGramStages][J][T]
     __shared__ const double *cols[kMaxCols];
-    __shared__ __align__(8) unsigned long long full[kGramStages];
+    __shared__ __align__(8) unsigned long long full[kGramStages], empty[kGramStages];
     const int J = 2 * h + 1;
     const long long npad = st->stride; // rows are zero-padded to a multiple of 32 doubles
-    for (int j = threadIdx.x; j < J; j += kThreads) cols[j] = basis_col(st, j, h);
+    for (int j = threadIdx.x; j < J; j += kWsThreads) cols[j] = basis_col(st, j, h);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kGramStages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < kGramStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kWsConsumerWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int NE = kGramWarps / NG;      // element groups
-    const int cg = warp % NG, eg = warp / NG;
-    double acc[CW][3];
-#pragma unroll
-    for (int c = 0; c < CW; ++c) acc[c][0] = acc[c][1] = acc[c][2] = 0.0;
-    const int r0 = h - 1, r1 = 2 * h - 1, r2 = 2 * h;
     const long long ntiles = (st->n + T - 1) / T;
     const size_t stage_doubles = (size_t)J * T;
     const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
-    auto issue = [&](long long k) { // warp 0 only
-        const long long t = blockIdx.x + k * (long long)gridDim.x;
-        const long long base = t * T;
-        long long valid = npad - base;
-        if (valid > T) valid = T;
-        const int stage = (int)(k % kGramStages);
-        double *dst = tile + stage * stage_doubles;
-        if (lane == 0) mbar_expect_tx(&full[stage], (unsigned)(J * valid * sizeof(double)));
-        __syncwarp();
-        for (int j = lane; j < J; j += 32)
-            tma_load_1d(dst + (size_t)j * T, cols[j] + base, (unsigned)(valid * sizeof(double)), &full[stage]);
-    };
-
-    if (warp == 0)
-        for (long long k = 0; k < kGramStages - 1 && k < my_tiles; ++k) issue(k);
-    for (long long k = 0; k < my_tiles; ++k) {
-        if (warp == 0 && k + kGramStages - 1 < my_tiles) issue(k + kGramStages - 1);
-        const int stage = (int)(k % kGramStages);
-        mbar_wait(&full[stage], (unsigned)((k / kGramStages) & 1));
-        const long long base = (blockIdx.x + k * (long long)gridDim.x) * T;
-        long long valid = npad - base;
-        if (valid > T) valid = T;
-        const double2 *cur = reinterpret_cast<const double2 *>(tile + stage * stage_doubles);
-        const int T2 = T >> 1, slice2 = T2 / NE; // double2 items per vector / per element group
-        const int e_end = min((eg + 1) * slice2, (int)(valid >> 1));
-        for (int e = eg * slice2 + lane; e < e_end; e += 32) {
-            const double2 a0 = cur[r0 * T2 + e], a1 = cur[r1 * T2 + e], a2 = cur[r2 * T2 + e];
+    const int NE = kWsConsumerWarps / NG;
+    double acc[CW][3];
 #pragma unroll
-            for (int c = 0; c < CW; ++c) {
-                const int j = cg + c * NG;
-                if (j < J) {
-                    const double2 v = cur[j * T2 + e];
-                    acc[c][0] = fma(a0.y, v.y, fma(a0.x, v.x, acc[c][0]));
-                    acc[c][1] = fma(a1.y, v.y, fma(a1.x, v.x, acc[c][1]));
-                    acc[c][2] = fma(a2.y, v.y, fma(a2.x, v.x, acc[c][2]));
+    for (int c = 0; c < CW; ++c) acc[c][0] = acc[c][1] = acc[c][2] = 0.0;
+    const int cw = warp - 1, cg = cw % NG, eg = cw / NG; // consumer coordinates (warp >= 1)
+
+    if (warp == 0) {
+        // ---------------- producer ----------------
+        for (long long k = 0; k < my_tiles; ++k) {
+            const int stage = (int)(k % kGramStages);
+            if (k >= kGramStages) mbar_wait(&empty[stage], (unsigned)(((k / kGramStages) - 1) & 1));
+            const long long base = (blockIdx.x + k * (long long)gridDim.x) * T;
+            long long valid = npad - base;
+            if (valid > T) valid = T;
+            double *dst = tile + stage * stage_doubles;
+            if (lane == 0) mbar_expect_tx(&full[stage], (unsigned)(J * valid * sizeof(double)));
+            __syncwarp();
+            for (int j = lane; j < J; j += 32)
+                tma_load_1d(dst + (size_t)j * T, cols[j] + base, (unsigned)(valid * sizeof(double)), &full[stage]);
+        }
+    } else {
+        // ---------------- consumers ----------------
+        const int r0 = h - 1, r1 = 2 * h - 1, r2 = 2 * h;
+        const int T2 = T >> 1, slice2 = T2 / NE;
+        for (long long k = 0; k < my_tiles; ++k) {
+            const int stage = (int)(k % kGramStages);
+            mbar_wait(&full[stage], (unsigned)((k / kGramStages) & 1));
+            const long long base = (blockIdx.x + k * (long long)gridDim.x) * T;
+            long long valid = npad - base;
+            if (valid > T) valid = T;
+            const double2 *cur = reinterpret_cast<const double2 *>(tile + stage * stage_doubles);
+            const int e_end = min((eg + 1) * slice2, (int)(valid >> 1));
+            for (int e = eg * slice2 + lane; e < e_end; e += 32) {
+                const double2 a0 = cur[r0 * T2 + e], a1 = cur[r1 * T2 + e], a2 = cur[r2 * T2 + e];
+#pragma unroll
+                for (int c = 0; c < CW; ++c) {
+                    const int j = cg + c * NG;
+                    if (j < J) {
+                        const double2 v = cur[j * T2 + e];
+                        acc[c][0] = fma(a0.y, v.y, fma(a0.x, v.x, acc[c][0]));
+                        acc[c][1] = fma(a1.y, v.y, fma(a1.x, v.x, acc[c][1]));
+                        acc[c][2] = fma(a2.y, v.y, fma(a2.x, v.x, acc[c][2]));
+                    }
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]); // this warp is done reading the stage
         }
-        __syncthreads(); // every warp is done with this stage before warp 0 refills it
     }
+    __syncthreads(); // all tiles consumed; the tile storage can be reused for the reduction
     // cross-warp reduction (fixed order over the NE element groups), one partial per (column,row)
-    double *red = tile; // [NE][J*3], reuses the (now idle) tile storage
+    double *red = tile; // [NE][J*3]
+    if (warp > 0) {
 #pragma unroll
-    for (int c = 0; c < CW; ++c) {
-        const int j = cg + c * NG;
-        if (j < J) { // warp-uniform
+        for (int c = 0; c < CW; ++c) {
+            const int j = cg + c * NG;
+            if (j < J) { // warp-uniform
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const double s = warp_sum(acc[c][r]);
-                if (lane == 0) red[eg * (J * 3) + j * 3 + r] = s;
+                for (int r = 0; r < 3; ++r) {
+                    const double s = warp_sum(acc[c][r]);
+                    if (lane == 0) red[eg * (J * 3) + j * 3 + r] = s;
+                }
             }
         }
     }
     __syncthreads();
-    for (int q = threadIdx.x; q < J * 3; q += kThreads) {
+    for (int q = threadIdx.x; q < J * 3; q += kWsThreads) {
         double s = 0.0;
         for (int g = 0; g < NE; ++g) s += red[g * (J * 3) + q];
         st->partials[(size_t)q * gridDim.x + blockIdx.x] = s;

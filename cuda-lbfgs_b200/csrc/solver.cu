@@ -193,7 +193,10 @@ static int launch_direction(lbfgsb200_solver *s)
             ClassTimer t(s, KC_GRAM);
             const size_t smem = s->gram_smem;
             if (s->gram_tma) {
-                k_gram_tma<kMaxCW><<<s->grid_gram, kThreads, smem, s->stream>>>(s->d_st, s->gram_T, s->gram_NG);
+                if ((2 * m + 1 + s->gram_NG - 1) / s->gram_NG <= 7)
+                    k_gram_tma<7><<<s->grid_gram, kWsThreads, smem, s->stream>>>(s->d_st, s->gram_T, s->gram_NG);
+                else
+                    k_gram_tma<kMaxCW><<<s->grid_gram, kWsThreads, smem, s->stream>>>(s->d_st, s->gram_T, s->gram_NG);
             } else {
                 const int G = s->gram_G, per = (2 * m + 1 + G - 1) / G, cwg = (per + kGramWarps - 1) / kGramWarps;
                 const dim3 grid(s->grid_gram, G);
@@ -586,15 +589,21 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     if (params->direction == LBFGSB200_DIR_COMPACT) {
         // shared-memory tile of all 2m+1 basis vectors; keep two CTAs per SM resident
         const int J = 2 * params->m + 1;
-        // pass A via TMA bulk copies is opt-in: measured on B200 (n=1e8, m=10) the cp.async pipeline
-        // reaches 6.75 TB/s, the 1 KB bulk copies of the TMA variant 4.0 TB/s
+        // Two implementations of pass A: the warp-specialised TMA kernel wins while the bulk
+        // copies stay large (few basis vectors => tiles of 512 elements, 4 KB per copy: 6.8-7.2 TB/s at
+        // m=3..5 vs 4.1-5.3 for cp.async); from m~8 on the column-grouped cp.async pipeline is faster
+        // (m=10: 6.4-6.9 vs 5.9 TB/s; m=50: 6.2 vs 2.4).  LBFGSB200_GRAM_TMA=0/1 forces one of them.
         const char *env = getenv("LBFGSB200_GRAM_TMA");
-        s->gram_tma = env ? atoi(env) : 0;
+        s->gram_tma = env ? atoi(env) : (params->m <= 6 ? 1 : 0);
         int Jt = J;
         if (s->gram_tma) {
+            // TMA variant: ONE CTA per SM owning (almost) all of shared memory: kGramStages stages of the
+            // largest tile that fits ~200 KB, so kGramStages-1 whole tiles per SM are in flight
+            const char *eb = getenv("LBFGSB200_GRAM_TMA_KB");
+            const size_t budget = (size_t)(eb ? atoi(eb) : 216) * 1024;
             s->gram_NS = kGramStages;
             s->gram_T = 512;
-            while (s->gram_T > 32 && (size_t)s->gram_NS * J * s->gram_T * sizeof(double) > 100 * 1024) s->gram_T >>= 1;
+            while (s->gram_T > 32 && (size_t)s->gram_NS * J * s->gram_T * sizeof(double) > budget) s->gram_T >>= 1;
         } else {
             // cp.async pipeline.  Large tiles matter (per-tile barrier/issue overhead): split the basis
             // into G column groups of <= ~40 columns (+3 row vectors when G > 1), take the largest T
@@ -611,17 +620,18 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
             if (es) s->gram_NS = atoi(es);
         }
         s->gram_smem = (size_t)s->gram_NS * Jt * s->gram_T * sizeof(double);
-        // TMA variant: 8 warps = NG column groups x NE element groups.  Each element group should
-        // span >= 32 double2 items (all lanes busy) and no warp may own more than kMaxCW columns.
+        // TMA variant: 16 consumer warps = NG column groups x NE element groups.  Each element group
+        // should span >= 32 double2 items (all lanes busy) and no warp may own more than kMaxCW columns.
         int NE = s->gram_T / 2 / 32;
         if (NE < 1) NE = 1;
-        if (NE > kGramWarps / 2) NE = kGramWarps / 2;
-        s->gram_NG = kGramWarps / NE;
-        while (s->gram_NG < kGramWarps && (J + s->gram_NG - 1) / s->gram_NG > kMaxCW) s->gram_NG <<= 1;
+        if (NE > kWsConsumerWarps / 2) NE = kWsConsumerWarps / 2;
+        s->gram_NG = kWsConsumerWarps / NE;
+        while (s->gram_NG < kWsConsumerWarps && (J + s->gram_NG - 1) / s->gram_NG > kMaxCW) s->gram_NG <<= 1;
         long long tiles = ((long long)s->n_local + s->gram_T - 1) / s->gram_T;
         const long long full = (long long)s->sms * kGramCtasPerSm;
         s->grid_combine = pick_grid((long long)s->n_local, s->sms, params->grid_ctas, kCombineCtasPerSm);
         long long gx = full / s->gram_G; // the G column groups share the resident-CTA slots
+        if (s->gram_tma) gx = s->sms; // warp-specialised: one CTA per SM
         if (gx < 1) gx = 1;
         s->grid_gram = params->grid_ctas > 0 ? params->grid_ctas : (int)(tiles < gx ? (tiles < 1 ? 1 : tiles) : gx);
     }
@@ -676,6 +686,7 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
         CREATE_TRY(cudaFuncSetAttribute(k_gram<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CREATE_TRY(cudaFuncSetAttribute(k_gram<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CREATE_TRY(cudaFuncSetAttribute(k_gram<kMaxCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CREATE_TRY(cudaFuncSetAttribute(k_gram_tma<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         CREATE_TRY(cudaFuncSetAttribute(k_gram_tma<kMaxCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     CREATE_TRY(cudaMalloc(&s->pkt, sizeof(double) * kPacket * (size_t)(nranks + 1)));
