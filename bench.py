@@ -220,6 +220,7 @@ def main():
     x0_pinned = pkg.PinnedArray(n_local)
     out_pinned = pkg.PinnedArray(n_local)
     pkg.x0_uniform(n_local, -2.0, 2.0, seed=42, offset=off, out=x0_pinned.array)
+    barrier()  # ranks generate shards of different offsets (mt19937 skip-ahead): line up before any exchange
 
     peak, peak_src = measured_peak()
     V = 8.0 * n_local

@@ -112,7 +112,7 @@ __device__ __forceinline__ unsigned long long global_ns()
 // 1-CTA scalar kernel.  On return rank r's payload is at mail_slot(st->mail, parity, r) (read it
 // with volatile loads); returns the parity.  Each rank runs on its own GPU, so the bounded spin
 // on the peers' flags is a real rendezvous; a peer that never arrives fails the launch (trap)
-// after 20 s instead of hanging the GPU.
+// after DevState::p2p_timeout_ns (default 120 s, LBFGSB200_P2P_TIMEOUT_S) instead of hanging the GPU.
 __device__ int p2p_allgather(DevState *st, const double *src, int count)
 {
     __shared__ unsigned long long s_seq;
@@ -136,7 +136,7 @@ __device__ int p2p_allgather(DevState *st, const double *src, int count)
         volatile unsigned long long *f = mail_flag(st->mail, par, threadIdx.x);
         const unsigned long long t0 = global_ns();
         while (*f < seq) {
-            if (global_ns() - t0 > 20000000000ull) __trap();
+            if (global_ns() - t0 > st->p2p_timeout_ns) __trap();
         }
     }
     __threadfence_system();

@@ -725,6 +725,8 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     st.stride = (long long)s->stride;
     if (comm && comm->p2p) {
         st.p2p = 1;
+        const char *et = getenv("LBFGSB200_P2P_TIMEOUT_S");
+        st.p2p_timeout_ns = (unsigned long long)(et ? atoi(et) : 120) * 1000000000ull;
         st.mail = comm->mail;
         st.peers = comm->peers_dev;
     }
@@ -901,7 +903,7 @@ int lbfgsb200_checkpoint_load(lbfgsb200_solver_t *s, const char *path)
     st.g = cur.g; st.w = cur.w; st.S = cur.S; st.Y = cur.Y;
     st.partials = cur.partials; st.send = cur.send; st.recv = cur.recv; st.trace = cur.trace;
     st.gram = cur.gram; st.gram_rows = cur.gram_rows; st.gram_recv = cur.gram_recv; st.delta = cur.delta;
-    st.mail = cur.mail; st.peers = cur.peers; st.p2p = cur.p2p;
+    st.mail = cur.mail; st.peers = cur.peers; st.p2p = cur.p2p; st.p2p_timeout_ns = cur.p2p_timeout_ns;
     st.cond_outer = cur.cond_outer; st.cond_inner = cur.cond_inner; st.use_graph = cur.use_graph;
     st.max_iterations = cur.max_iterations; st.tolerance = cur.tolerance; st.lsp = cur.lsp; // the new handle's limits apply
     if (st.status != LBFGSB200_CONVERGED && st.status != LBFGSB200_LS_FAILED && st.k < st.max_iterations) {

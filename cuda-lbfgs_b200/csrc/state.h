@@ -108,6 +108,7 @@ struct DevState {
     double *mail;    // this rank's mailbox
     double **peers;  // [nranks] mailbox pointers of all ranks (own entry == mail)
     int p2p;
+    unsigned long long p2p_timeout_ns; // bounded rendezvous: trap instead of hanging the GPU
 
     // ---- CUDA-graph mode: WHILE-node condition handles set by the scalar kernel ----
     unsigned long long cond_outer, cond_inner;
