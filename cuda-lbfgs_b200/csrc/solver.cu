@@ -455,7 +455,10 @@ static int do_iterate(lbfgsb200_solver *s, int64_t iterations)
     LB_TRY(snapshot(s));
     if (graph) { // kernel nodes executed: fixed part per iteration + 2 per trial
         const long long its = s->h_snapshot.k - k0, trials = s->h_snapshot.trial_evals - t0;
-        s->launches += (its + (s->h_snapshot.ctrl.done ? 1 : 0)) * s->graph_fixed_launches + 2 * trials;
+        // an exit at the top of / inside an iteration (converged, line search failed) still ran that
+        // iteration's nodes as no-ops; "maximum iterations" is raised by the last accept itself
+        const bool extra = s->h_snapshot.ctrl.done && s->h_snapshot.status != LBFGSB200_MAX_ITER;
+        s->launches += (its + (extra ? 1 : 0)) * s->graph_fixed_launches + 2 * trials;
         s->k_host += its;
     }
     float ms = 0.f;
@@ -682,12 +685,23 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
         const size_t total = gram_nb * gram_nb + gram_cnt * (size_t)(nranks + 1) + (size_t)(2 * params->m + 1);
         CREATE_TRY(cudaMalloc(&s->gram, sizeof(double) * total));
         CREATE_TRY(cudaMemsetAsync(s->gram, 0, sizeof(double) * total, s->stream));
-        const int smem = (int)s->gram_smem;
-        CREATE_TRY(cudaFuncSetAttribute(k_gram<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CREATE_TRY(cudaFuncSetAttribute(k_gram<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CREATE_TRY(cudaFuncSetAttribute(k_gram<kMaxCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CREATE_TRY(cudaFuncSetAttribute(k_gram_tma<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CREATE_TRY(cudaFuncSetAttribute(k_gram_tma<kMaxCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        // opt every pass-A variant in to the device's full dynamic shared memory once (the limit is per
+        // function and process-wide; occupancy still follows the size actually passed at launch)
+        int dev = 0, optin = 0;
+        CREATE_TRY(cudaGetDevice(&dev));
+        CREATE_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        if ((size_t)optin < s->gram_smem + 4096) {
+            set_error("pass A needs %zu bytes of shared memory, the device offers %d", s->gram_smem, optin);
+            lbfgsb200_destroy(s);
+            return LBFGSB200_ERR_INVALID;
+        }
+        const void *variants[] = {(const void *)k_gram<3>, (const void *)k_gram<6>, (const void *)k_gram<kMaxCW>,
+                                  (const void *)k_gram_tma<7>, (const void *)k_gram_tma<kMaxCW>};
+        for (const void *fn : variants) {
+            cudaFuncAttributes fa;
+            CREATE_TRY(cudaFuncGetAttributes(&fa, fn));
+            CREATE_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+        }
     }
     CREATE_TRY(cudaMalloc(&s->pkt, sizeof(double) * kPacket * (size_t)(nranks + 1)));
     CREATE_TRY(cudaMemsetAsync(s->pkt, 0, sizeof(double) * kPacket * (size_t)(nranks + 1), s->stream));

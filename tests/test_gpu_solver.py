@@ -295,3 +295,23 @@ def test_checkpoint_resume_is_bitwise(gpu, tmp_path, direction, graph):
     with pytest.raises(gpu.LbfgsError, match="different shape"):
         c.load(path)
     c.destroy()
+
+
+def test_solvers_of_different_history_sizes_coexist(gpu):
+    """Pass A opts into large dynamic shared memory per FUNCTION (process-wide): a second solver with
+    another m / another pass-A variant must not invalidate the first one's launches."""
+    x0 = gpu.x0_uniform(40000, -2, 2)
+    mk = lambda m: gpu.Solver("rosenbrock", 40000, gpu.default_params("par", line_search="wolfe", m=m, max_iterations=100,
+                                                                      direction="compact"), trace_rows=0)
+    a, b, c = mk(3), mk(10), mk(40)   # TMA variant, cp.async, cp.async with column groups
+    for s in (a, b, c):
+        s.set_x0(x0)
+    for _ in range(3):
+        for s in (c, a, b):
+            s.iterate(5)
+    ref = {}
+    for m in (3, 10, 40):
+        ref[m], _, _ = gpu.solve("rosenbrock", x0, "wolfe", "par", m=m, max_iterations=15, direction="compact")
+    for s, m in ((a, 3), (b, 10), (c, 40)):
+        assert np.array_equal(s.x(), ref[m]), m
+        s.destroy()
