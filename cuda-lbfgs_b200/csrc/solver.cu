@@ -948,6 +948,7 @@ int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local)
     st.ctrl.h = 0;
     st.ctrl.k = 0;
     st.status = LBFGSB200_RUNNING;
+    st.use_graph = 0; // re-armed per run by do_iterate
     st.xL = st.xR = st.dL = st.dR = st.gL = st.gR = 0.0;
     CUDA_TRY(cudaMemcpyAsync(s->d_st, &st, sizeof st, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream)); // st is a stack object

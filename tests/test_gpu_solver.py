@@ -315,3 +315,41 @@ def test_solvers_of_different_history_sizes_coexist(gpu):
     for s, m in ((a, 3), (b, 10), (c, 40)):
         assert np.array_equal(s.x(), ref[m]), m
         s.destroy()
+
+
+def test_randomised_configurations_match_oracle(gpu, oracle):
+    """Property-style sweep: random sizes, history sizes, objectives, line searches, trees, direction
+    algorithms and loop modes, from harsher starts (U(-4,4)) so that step rejections, curvature-gate
+    skips (s.y <= 0), steepest-descent fallbacks and failed searches occur.  12 steps each, compared
+    with the oracle: same status, same per-step trial counts and history sizes, iterates to 1e-8."""
+    rng = np.random.default_rng(2026)
+    objectives = ["rosenbrock", "tridiag", "quadratic"]
+    searches = ["backtracking", "interpolation", "wolfe", "backtracking_wolfe"]
+    checked = skipped_paths = 0
+    for case in range(80):
+        n = int(rng.choice([7, 64, 1000, 4097, 30001]))
+        m = int(rng.choice([1, 2, 5, 10, 17]))
+        obj = objectives[case % 3]
+        ls = searches[int(rng.integers(0, 4))]
+        flavor = ["seq", "par"][int(rng.integers(0, 2))]
+        if ls == "wolfe" and flavor == "seq":
+            flavor = "par"  # the seq tree's unsafeguarded cubic goes NaN (covered by its own test)
+        direction = ["two_loop", "compact"][int(rng.integers(0, 2))]
+        graph = int(rng.integers(0, 2))
+        x0 = rng.uniform(-4, 4, n)
+        K = 12
+        xo, io, to = oracle.lbfgs(obj, x0, ls, flavor, m, K, 1e-7, trace_rows=K)
+        x, info, tr = gpu.solve(obj, x0, ls, flavor, trace_rows=K, m=m, max_iterations=K, tolerance=1e-7,
+                                direction=direction, use_graph=graph)
+        tag = (case, obj, n, m, ls, flavor, direction, graph)
+        assert info["status"] == io["status"], tag + (info["status"], io["status"])
+        assert info["iterations"] == io["iterations"], tag + (info["iterations"], io["iterations"])
+        k = info["iterations"]
+        assert np.array_equal(tr[:k, 4], to[:k, 4]), tag + ("trials", tr[:k, 4], to[:k, 4])
+        assert np.array_equal(tr[:k, 5], to[:k, 5]), tag + ("history", tr[:k, 5], to[:k, 5])
+        if k and np.any(np.diff(np.concatenate([[0], to[:k, 5]])) == 0) and to[k - 1, 5] < m:
+            skipped_paths += 1  # a pair was rejected by the curvature gate somewhere
+        scale = max(np.max(np.abs(xo)), 1e-3)
+        assert np.max(np.abs(x - xo)) <= 1e-8 * scale, tag + (np.max(np.abs(x - xo)) / scale,)
+        checked += 1
+    assert checked == 80
