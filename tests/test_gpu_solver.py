@@ -353,3 +353,31 @@ def test_randomised_configurations_match_oracle(gpu, oracle):
         assert np.max(np.abs(x - xo)) <= 1e-8 * scale, tag + (np.max(np.abs(x - xo)) / scale,)
         checked += 1
     assert checked == 80
+
+
+@pytest.mark.parametrize("direction", ["two_loop", "compact"])
+def test_curvature_gate_skip_path(gpu, oracle, direction):
+    """seq/lbfgs.cpp:182-195: a pair with s.y <= 0 is NOT stored.  These seeded starts hit that branch
+    (found with the oracle); the candidate pair then sits in the spare ring slot and is dropped, the
+    next direction needs s_newest . g for a pair the accept kernel did not produce (k_dot_sg path),
+    and with a full ring the oldest pair must survive."""
+    hit = 0
+    for seed, n in ((35, 6), (33, 50)):
+        rng = np.random.default_rng(seed)
+        assert int(rng.choice([6, 20, 50])) == n  # same draw order as the search that found these seeds
+        x0 = rng.uniform(-4, 4, n)
+        for ls, flavor in (("backtracking", "seq"), ("interpolation", "par")):
+            for m in (30, 3):
+                K = 25
+                xo, io, to = oracle.lbfgs("rosenbrock", x0, ls, flavor, m, K, 1e-9, trace_rows=K)
+                grew = np.diff(np.concatenate([[0], to[:, 5]]))
+                if m == 30:
+                    assert np.any(grew == 0), "the oracle no longer skips a pair here"
+                    hit += 1
+                x, info, tr = gpu.solve("rosenbrock", x0, ls, flavor, trace_rows=K, m=m, max_iterations=K, tolerance=1e-9,
+                                        direction=direction)
+                assert info["status"] == io["status"] and info["iterations"] == io["iterations"]
+                assert np.array_equal(tr[:, 5], to[:, 5]), (seed, ls, m, tr[:, 5], to[:, 5])
+                assert np.array_equal(tr[:, 4], to[:, 4]), (seed, ls, m)
+                assert relvec(x, xo) <= 1e-8, (seed, ls, m, relvec(x, xo))
+    assert hit == 4
