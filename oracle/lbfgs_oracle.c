@@ -599,6 +599,93 @@ int oracle_lbfgs(const oracle_params_t *p, size_t n, const double *x0, double *x
 }
 
 /* ------------------------------------------------------------------ */
+/* CUDA-tree outer loop: par/L-BFGS.cu:195-357 (see the header: unpinned) */
+/* ------------------------------------------------------------------ */
+int oracle_lbfgs_cuda_profile(const oracle_params_t *p, size_t n, const double *x0, double *x_out,
+                              double *trace, size_t trace_rows, oracle_result_t *res)
+{
+    const int m = p->m;
+    long nf = 0, ng = 0;
+    int status = ORACLE_STATUS_MAX_ITER;
+    double *x = (double *)malloc(n * sizeof(double)), *g = (double *)malloc(n * sizeof(double));
+    double *d = (double *)malloc(n * sizeof(double)), *q = (double *)malloc(n * sizeof(double));
+    double *xn = (double *)malloc(n * sizeof(double)), *gn = (double *)malloc(n * sizeof(double));
+    double *xt = (double *)malloc(n * sizeof(double)), *gt = (double *)malloc(n * sizeof(double));
+    double *S = (double *)calloc((size_t)m * n, sizeof(double)), *Y = (double *)calloc((size_t)m * n, sizeof(double));
+    double *alpha = (double *)calloc(m, sizeof(double)), *rho = (double *)calloc(m, sizeof(double));
+    int *skip = (int *)calloc(m, sizeof(int));
+    memcpy(x, x0, n * sizeof(double));
+    double f_cur = oracle_f(p->objective, x, n); nf++;
+    oracle_grad(p->objective, x, g, n); ng++; /* :199 */
+    int k;
+    for (k = 0; k < p->max_iterations; ++k) {
+        if (k == 0) {
+            for (size_t j = 0; j < n; ++j) d[j] = -g[j]; /* :208 */
+        } else {
+            memcpy(q, g, n * sizeof(double)); /* :212 */
+            const int lo = k - m > 0 ? k - m : 0;
+            for (int i = k - 1; i >= lo; --i) { /* :216-236 */
+                const double *s = S + (size_t)(i % m) * n, *y = Y + (size_t)(i % m) * n;
+                const double si_yi = oracle_dot(s, y, n);
+                skip[i % m] = si_yi <= 1e-10; /* :222-223 */
+                if (skip[i % m]) continue;
+                rho[i % m] = 1.0 / si_yi;
+                alpha[i % m] = rho[i % m] * oracle_dot(s, q, n);
+                for (size_t j = 0; j < n; ++j) q[j] -= alpha[i % m] * y[j];
+            }
+            const int last = (k - 1) % m; /* :239-255 */
+            const double ys = oracle_dot(S + (size_t)last * n, Y + (size_t)last * n, n);
+            const double yy = oracle_dot(Y + (size_t)last * n, Y + (size_t)last * n, n);
+            const double gamma = (yy > 0 && ys > 1e-10) ? ys / yy : 1.0;
+            for (size_t j = 0; j < n; ++j) q[j] *= gamma;
+            for (int i = lo; i < k; ++i) { /* :263-274 */
+                if (skip[i % m]) continue; /* (the reference would reuse stale rho/alpha here) */
+                const double *s = S + (size_t)(i % m) * n, *y = Y + (size_t)(i % m) * n;
+                const double beta = rho[i % m] * oracle_dot(y, q, n);
+                const double c = alpha[i % m] - beta;
+                for (size_t j = 0; j < n; ++j) q[j] += s[j] * c;
+            }
+            for (size_t j = 0; j < n; ++j) d[j] = -q[j]; /* :276 */
+        }
+        vec_ctx_t c = { p->objective, n, x, d, xt, gt };
+        phi_t phi;
+        memset(&phi, 0, sizeof phi);
+        phi.f_at = vec_f; phi.df_at = vec_df; phi.f0 = vec_f0;
+        phi.gd = oracle_dot(g, d, n); phi.ctx = &c;
+        const double a = run_ls(p->line_search, p->flavor, &phi); /* :293 (with the CURRENT gradient) */
+        nf += phi.nf; ng += phi.ng;
+        if (a < 1e-10) { status = ORACLE_STATUS_LS_FAILED; break; } /* :295-305 */
+        for (size_t j = 0; j < n; ++j) xn[j] = x[j] + a * d[j]; /* :309 (no FMA restated) */
+        oracle_grad(p->objective, xn, gn, n); ng++;              /* :323 */
+        double *s = S + (size_t)(k % m) * n, *y = Y + (size_t)(k % m) * n; /* :332-333 */
+        for (size_t j = 0; j < n; ++j) { s[j] = xn[j] - x[j]; y[j] = gn[j] - g[j]; }
+        memcpy(x, xn, n * sizeof(double));
+        memcpy(g, gn, n * sizeof(double));
+        f_cur = oracle_f(p->objective, x, n); nf++; /* :351 (printed only) */
+        const double norm_g = sqrt(oracle_dot(g, g, n)); /* :346-347 */
+        if (trace && (size_t)k < trace_rows) {
+            double *row = trace + (size_t)k * ORACLE_TRACE_COLS;
+            row[ORACLE_TR_K] = (double)k; row[ORACLE_TR_F] = f_cur; row[ORACLE_TR_GNORM] = norm_g;
+            row[ORACLE_TR_ALPHA] = a; row[ORACLE_TR_TRIALS] = (double)phi.ntrial;
+            row[ORACLE_TR_HIST] = (double)(k + 1 < m ? k + 1 : m);
+            row[ORACLE_TR_X0] = x[0]; row[ORACLE_TR_XMID] = x[n / 2];
+        }
+        if (norm_g <= p->tolerance) { status = ORACLE_STATUS_CONVERGED; ++k; break; } /* :353-357 */
+    }
+    if (x_out) memcpy(x_out, x, n * sizeof(double));
+    if (res) {
+        res->status = status; res->iterations = k; res->f_evals = nf; res->g_evals = ng;
+        res->f = oracle_f(p->objective, x, n);
+        oracle_grad(p->objective, x, gn, n);
+        res->gnorm = oracle_norm(gn, n);
+    }
+    free(x); free(g); free(d); free(q); free(xn); free(gn); free(xt); free(gt);
+    free(S); free(Y); free(alpha); free(rho); free(skip);
+    (void)f_cur;
+    return status;
+}
+
+/* ------------------------------------------------------------------ */
 /* x0 generator: libstdc++ mt19937 + uniform_real_distribution<double>  */
 /* (seq/main.cpp:34-43, par/L-BFGS-Wolfe.cu:458-465)                    */
 /* ------------------------------------------------------------------ */

@@ -56,6 +56,8 @@ class Oracle:
         L.oracle_lbfgs.restype = C.c_int
         L.oracle_lbfgs.argtypes = [C.POINTER(_Params), C.c_size_t, _dp, _dp, _dp, C.c_size_t,
                                    C.POINTER(_Result)]
+        L.oracle_lbfgs_cuda_profile.restype = C.c_int
+        L.oracle_lbfgs_cuda_profile.argtypes = L.oracle_lbfgs.argtypes
         L.oracle_dot.restype = C.c_double
         L.oracle_dot.argtypes = [_dp, _dp, C.c_size_t]
         L.oracle_norm.restype = C.c_double
@@ -121,14 +123,14 @@ class Oracle:
         return a, nf.value, ng.value
 
     def lbfgs(self, objective, x0, line_search="backtracking", flavor="seq", m=10,
-              max_iterations=1000, tolerance=1e-5, trace_rows=0):
+              max_iterations=1000, tolerance=1e-5, trace_rows=0, profile="seq"):
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         p = _Params(OBJ[objective], LS[line_search], FLAVOR[flavor], m, max_iterations, tolerance)
         r = _Result()
         x = np.empty_like(x0)
         trace = np.zeros((max(trace_rows, 1), TRACE_COLS), dtype=np.float64)
-        self.L.oracle_lbfgs(C.byref(p), x0.size, _p(x0), _p(x), _p(trace) if trace_rows else None,
-                            trace_rows, C.byref(r))
+        fn = self.L.oracle_lbfgs if profile == "seq" else self.L.oracle_lbfgs_cuda_profile
+        fn(C.byref(p), x0.size, _p(x0), _p(x), _p(trace) if trace_rows else None, trace_rows, C.byref(r))
         info = dict(status=r.status, iterations=r.iterations, f_evals=r.f_evals,
                     g_evals=r.g_evals, f=r.f, gnorm=r.gnorm)
         rows = min(trace_rows, r.iterations)

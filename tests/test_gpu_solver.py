@@ -381,3 +381,31 @@ def test_curvature_gate_skip_path(gpu, oracle, direction):
                 assert np.array_equal(tr[:, 4], to[:, 4]), (seed, ls, m)
                 assert relvec(x, xo) <= 1e-8, (seed, ls, m, relvec(x, xo))
     assert hit == 4
+
+
+@pytest.mark.parametrize("direction", ["two_loop", "compact"])
+def test_cuda_profile_matches_its_restatement(gpu, oracle, direction):
+    """profile=CUDA (par/L-BFGS.cu outer loop: slot always overwritten, pairs with s.y<=1e-10 skipped,
+    gamma fallback, <= test after the step, no descent safeguard) against oracle_lbfgs_cuda_profile.
+    That restatement is unpinned (the CUDA reference cannot run in the build container) and omits the
+    reference's stale-state bugs, exactly like the product; this checks the two agree with each other,
+    including on starts where pairs with negative curvature are stored and skipped."""
+    cases = [("rosenbrock", 10000, (-2, 2), "wolfe", 10, 20, None), ("tridiag", 10000, (-2, 2), "interpolation", 5, 30, None),
+             ("rosenbrock", 6, (-4, 4), "backtracking", 30, 25, 35), ("rosenbrock", 50, (-4, 4), "interpolation", 3, 25, 33),
+             ("quadratic", 5000, (-1000, 1000), "backtracking", 10, 10, None)]
+    for obj, n, (lo, hi), ls, m, K, seed in cases:
+        if seed is None:
+            x0 = oracle.x0(n, lo, hi)
+        else:
+            rng = np.random.default_rng(seed)
+            rng.choice([6, 20, 50])
+            x0 = rng.uniform(lo, hi, n)
+        xo, io, to = oracle.lbfgs(obj, x0, ls, "par", m, K, 1e-6, trace_rows=K, profile="cuda")
+        x, info, tr = gpu.solve(obj, x0, ls, "par", trace_rows=K, m=m, max_iterations=K, tolerance=1e-6, profile="cuda",
+                                direction=direction)
+        tag = (obj, n, ls, m, direction)
+        assert info["status"] == io["status"], tag + (info["status"], io["status"])
+        assert info["iterations"] == io["iterations"], tag + (info["iterations"], io["iterations"])
+        k = info["iterations"]
+        assert np.array_equal(tr[:k, 4], to[:k, 4]) and np.array_equal(tr[:k, 5], to[:k, 5]), tag
+        assert np.max(np.abs(x - xo)) <= 1e-8 * max(np.max(np.abs(xo)), 1e-3), tag
