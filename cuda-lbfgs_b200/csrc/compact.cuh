@@ -21,6 +21,7 @@
 // then each warp owns every 8th column and each lane every 32nd element, so the number of
 // accumulators per thread is independent of h.
 #pragma once
+#include <cuda.h> // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 
 #include "kernels.cuh"
@@ -292,6 +293,125 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_gram_tma(const DevState *__re
         for (int c = 0; c < CW; ++c) {
             const int j = cg + c * NG;
             if (j < J) { // warp-uniform
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const double s = warp_sum(acc[c][r]);
+                    if (lane == 0) red[eg * (J * 3) + j * 3 + r] = s;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < J * 3; q += kWsThreads) {
+        double s = 0.0;
+        for (int g = 0; g < NE; ++g) s += red[g * (J * 3) + q];
+        st->partials[(size_t)q * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+// ---- pass A, tensor-map TMA variant ---------------------------------------------------------
+// The (s, y) ring buffers are 2-D tensors [slot][element] with a fixed row stride, and the window
+// of stored pairs is a circular range of slots, i.e. at most two runs of consecutive rows.  So a
+// whole tile of the history -- up to m rows x T elements per array -- is fetched with at most FIVE
+// tiled TMA loads (cp.async.bulk.tensor.2d, SASS UTMALDG): S run A, S run B, Y run A, Y run B, g,
+// instead of 2h+1 one-row bulk copies.  Tensor maps are built on the host per possible run length
+// (the box shape is part of the map) and live in global memory.  Out-of-range columns of the last
+// tile are zero-filled by the TMA unit, and the transaction count is always the full box.
+// Producer / consumer structure, tile layout and arithmetic are those of k_gram_tma.
+struct GramMaps {          // device array, one entry per run length r = 1..nslots (index r)
+    CUtensorMap s[kMaxSlots + 1];
+    CUtensorMap y[kMaxSlots + 1];
+    CUtensorMap g;         // 1 x T box over the gradient
+};
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1,
+                                            unsigned long long *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <int CW>
+__global__ void __launch_bounds__(kWsThreads, 1)
+k_gram_tma2d(const DevState *__restrict__ st, const GramMaps *__restrict__ maps, int T, int NG)
+{
+    const int h = st->h;
+    if (st->ctrl.done || st->steepest || h == 0) return;
+    extern __shared__ __align__(128) double tile[]; // [kGramStages][J][T]
+    __shared__ __align__(8) unsigned long long full[kGramStages], empty[kGramStages];
+    const int J = 2 * h + 1;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGramStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kWsConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long ntiles = (st->n + T - 1) / T;
+    const size_t stage_doubles = (size_t)J * T;
+    const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int NE = kWsConsumerWarps / NG;
+    double acc[CW][3];
+#pragma unroll
+    for (int c = 0; c < CW; ++c) acc[c][0] = acc[c][1] = acc[c][2] = 0.0;
+    const int cw = warp - 1, cg = cw % NG, eg = cw / NG;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // window = slots base .. base+h-1 (mod nslots): run A = [base, base+ra), run B = [0, rb)
+            const int ns = st->nslots, base_slot = st->base;
+            const int ra = min(h, ns - base_slot), rb = h - ra;
+            const unsigned bytes = (unsigned)(J * T * sizeof(double));
+            for (long long k = 0; k < my_tiles; ++k) {
+                const int stage = (int)(k % kGramStages);
+                if (k >= kGramStages) mbar_wait(&empty[stage], (unsigned)(((k / kGramStages) - 1) & 1));
+                const int col = (int)((blockIdx.x + k * (long long)gridDim.x) * T);
+                double *dst = tile + stage * stage_doubles;
+                mbar_expect_tx(&full[stage], bytes);
+                tma_load_2d(dst, &maps->s[ra], col, base_slot, &full[stage]);
+                if (rb) tma_load_2d(dst + (size_t)ra * T, &maps->s[rb], col, 0, &full[stage]);
+                tma_load_2d(dst + (size_t)h * T, &maps->y[ra], col, base_slot, &full[stage]);
+                if (rb) tma_load_2d(dst + (size_t)(h + ra) * T, &maps->y[rb], col, 0, &full[stage]);
+                tma_load_2d(dst + (size_t)(2 * h) * T, &maps->g, col, 0, &full[stage]);
+            }
+        }
+    } else {
+        const int r0 = h - 1, r1 = 2 * h - 1, r2 = 2 * h;
+        const int T2 = T >> 1, slice2 = T2 / NE;
+        for (long long k = 0; k < my_tiles; ++k) {
+            const int stage = (int)(k % kGramStages);
+            mbar_wait(&full[stage], (unsigned)((k / kGramStages) & 1));
+            const double2 *cur = reinterpret_cast<const double2 *>(tile + stage * stage_doubles);
+            const int e_end = (eg + 1) * slice2; // columns beyond n were zero-filled by the TMA unit
+            for (int e = eg * slice2 + lane; e < e_end; e += 32) {
+                const double2 a0 = cur[r0 * T2 + e], a1 = cur[r1 * T2 + e], a2 = cur[r2 * T2 + e];
+#pragma unroll
+                for (int c = 0; c < CW; ++c) {
+                    const int j = cg + c * NG;
+                    if (j < J) {
+                        const double2 v = cur[j * T2 + e];
+                        acc[c][0] = fma(a0.y, v.y, fma(a0.x, v.x, acc[c][0]));
+                        acc[c][1] = fma(a1.y, v.y, fma(a1.x, v.x, acc[c][1]));
+                        acc[c][2] = fma(a2.y, v.y, fma(a2.x, v.x, acc[c][2]));
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+        }
+    }
+    __syncthreads();
+    double *red = tile; // [NE][J*3]
+    if (warp > 0) {
+#pragma unroll
+        for (int c = 0; c < CW; ++c) {
+            const int j = cg + c * NG;
+            if (j < J) {
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     const double s = warp_sum(acc[c][r]);

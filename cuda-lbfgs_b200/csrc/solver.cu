@@ -92,6 +92,7 @@ struct lbfgsb200_solver {
     int gram_T = 512;           // compact form: elements per vector per shared-memory tile
     int gram_tma = 0, gram_NG = 2, gram_NS = 2, gram_G = 1; // pass A: cp.async pipeline (default) or TMA bulk copies
     size_t gram_smem = 0;
+    GramMaps *gram_maps = nullptr; // device: tensor maps of the tensor-map TMA variant (gram_tma == 2)
     double *gram = nullptr;     // compact form: Gram matrix + pass-A rows + delta + all-gather buffer
     lbfgsb200_params_t params;
     lbfgsb200_comm *comm = nullptr;
@@ -192,7 +193,12 @@ static int launch_direction(lbfgsb200_solver *s)
         {
             ClassTimer t(s, KC_GRAM);
             const size_t smem = s->gram_smem;
-            if (s->gram_tma) {
+            if (s->gram_tma == 2) {
+                if ((2 * m + 1 + s->gram_NG - 1) / s->gram_NG <= 7)
+                    k_gram_tma2d<7><<<s->grid_gram, kWsThreads, smem, s->stream>>>(s->d_st, s->gram_maps, s->gram_T, s->gram_NG);
+                else
+                    k_gram_tma2d<kMaxCW><<<s->grid_gram, kWsThreads, smem, s->stream>>>(s->d_st, s->gram_maps, s->gram_T, s->gram_NG);
+            } else if (s->gram_tma) {
                 if ((2 * m + 1 + s->gram_NG - 1) / s->gram_NG <= 7)
                     k_gram_tma<7><<<s->grid_gram, kWsThreads, smem, s->stream>>>(s->d_st, s->gram_T, s->gram_NG);
                 else
@@ -540,6 +546,46 @@ void lbfgsb200_shard_range(size_t n_global, int rank, int nranks, size_t *offset
     if (n_local) *n_local = len;
 }
 
+// Tensor maps for the tensor-map TMA variant of pass A: S and Y are [nslots][stride] row-major FP64
+// tensors; one map per run length r (box = T columns x r rows), plus a 1-row map over g.
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int build_gram_maps(lbfgsb200_solver *s, const DevState &st)
+{
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+        set_error("cuTensorMapEncodeTiled is not available");
+        cudaGetLastError();
+        return LBFGSB200_ERR_CUDA;
+    }
+    encode_tiled_fn encode = (encode_tiled_fn)fn;
+    GramMaps *host = new GramMaps;
+    memset(host, 0, sizeof *host);
+    auto make = [&](CUtensorMap *out, double *base, int rows_total, int box_rows) -> bool {
+        const cuuint64_t gdim[2] = {(cuuint64_t)s->stride, (cuuint64_t)rows_total};
+        const cuuint64_t gstride[1] = {(cuuint64_t)s->stride * sizeof(double)};
+        const cuuint32_t box[2] = {(cuuint32_t)s->gram_T, (cuuint32_t)box_rows};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) set_error("cuTensorMapEncodeTiled failed with %d (rows %d, box %d x %d)", (int)r, rows_total, s->gram_T, box_rows);
+        return r == CUDA_SUCCESS;
+    };
+    bool ok = true;
+    for (int r = 1; r <= s->nslots && ok; ++r) ok = make(&host->s[r], st.S, s->nslots, r) && make(&host->y[r], st.Y, s->nslots, r);
+    ok = ok && make(&host->g, st.g, 1, 1);
+    int rc = 0;
+    if (!ok) rc = LBFGSB200_ERR_CUDA;
+    if (!rc && cudaMalloc(&s->gram_maps, sizeof(GramMaps)) != cudaSuccess) rc = LBFGSB200_ERR_NOMEM;
+    if (!rc && cudaMemcpy(s->gram_maps, host, sizeof(GramMaps), cudaMemcpyHostToDevice) != cudaSuccess) rc = LBFGSB200_ERR_CUDA;
+    delete host;
+    return rc;
+}
+
 static int check_params(const lbfgsb200_params_t *p)
 {
     if (!p) { set_error("params is NULL"); return LBFGSB200_ERR_INVALID; }
@@ -592,12 +638,15 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     if (params->direction == LBFGSB200_DIR_COMPACT) {
         // shared-memory tile of all 2m+1 basis vectors; keep two CTAs per SM resident
         const int J = 2 * params->m + 1;
-        // Two implementations of pass A: the warp-specialised TMA kernel wins while the bulk
-        // copies stay large (few basis vectors => tiles of 512 elements, 4 KB per copy: 6.8-7.2 TB/s at
-        // m=3..5 vs 4.1-5.3 for cp.async); from m~8 on the column-grouped cp.async pipeline is faster
-        // (m=10: 6.4-6.9 vs 5.9 TB/s; m=50: 6.2 vs 2.4).  LBFGSB200_GRAM_TMA=0/1 forces one of them.
+        // Three implementations of pass A, picked by history size, LBFGSB200_GRAM_TMA forces one:
+        //   2  tensor-map TMA (UTMALDG.2D): <= 5 tiled loads per tile of the whole history.  Default for
+        //      m > 6: 7.0-7.3 TB/s at m = 10..50 (1.07-1.11x the measured copy peak)
+        //   1  one-row bulk copies (UBLKCP), tiles of 512 elements.  Default for m <= 6: 6.8-7.2 TB/s
+        //   0  cp.async (LDGSTS) pipeline with column groups: 6.1-6.9 TB/s; fallback when the tensor maps
+        //      cannot be built (shards of 2^31 elements or more: TMA coordinates are 32-bit)
         const char *env = getenv("LBFGSB200_GRAM_TMA");
-        s->gram_tma = env ? atoi(env) : (params->m <= 6 ? 1 : 0);
+        s->gram_tma = env ? atoi(env) : (params->m <= 6 ? 1 : 2);
+        if (s->gram_tma == 2 && s->stride >= ((size_t)1 << 31)) s->gram_tma = 0;
         int Jt = J;
         if (s->gram_tma) {
             // TMA variant: ONE CTA per SM owning (almost) all of shared memory: kGramStages stages of the
@@ -605,7 +654,7 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
             const char *eb = getenv("LBFGSB200_GRAM_TMA_KB");
             const size_t budget = (size_t)(eb ? atoi(eb) : 216) * 1024;
             s->gram_NS = kGramStages;
-            s->gram_T = 512;
+            s->gram_T = s->gram_tma == 2 ? 256 : 512; // a TMA box dimension is at most 256 elements
             while (s->gram_T > 32 && (size_t)s->gram_NS * J * s->gram_T * sizeof(double) > budget) s->gram_T >>= 1;
         } else {
             // cp.async pipeline.  Large tiles matter (per-tile barrier/issue overhead): split the basis
@@ -696,7 +745,8 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
             return LBFGSB200_ERR_INVALID;
         }
         const void *variants[] = {(const void *)k_gram<3>, (const void *)k_gram<6>, (const void *)k_gram<kMaxCW>,
-                                  (const void *)k_gram_tma<7>, (const void *)k_gram_tma<kMaxCW>};
+                                  (const void *)k_gram_tma<7>, (const void *)k_gram_tma<kMaxCW>,
+                                  (const void *)k_gram_tma2d<7>, (const void *)k_gram_tma2d<kMaxCW>};
         for (const void *fn : variants) {
             cudaFuncAttributes fa;
             CREATE_TRY(cudaFuncGetAttributes(&fa, fn));
@@ -766,6 +816,10 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     st.lsp.bt_tol = params->backtracking_tol;
     st.lsp.wolfe_min = params->wolfe_min;
     st.status = LBFGSB200_RUNNING;
+    if (s->gram && s->gram_tma == 2) {
+        int rc_maps = build_gram_maps(s, st);
+        if (rc_maps < 0) { lbfgsb200_destroy(s); return rc_maps; }
+    }
     CREATE_TRY(cudaMemcpyAsync(s->d_st, &st, sizeof st, cudaMemcpyHostToDevice, s->stream));
     CREATE_TRY(cudaStreamSynchronize(s->stream));
 #undef CREATE_TRY
@@ -782,6 +836,7 @@ void lbfgsb200_destroy(lbfgsb200_solver_t *s)
     if (s->arena) cudaFree(s->arena);
     if (s->partials) cudaFree(s->partials);
     if (s->gram) cudaFree(s->gram);
+    if (s->gram_maps) cudaFree(s->gram_maps);
     if (s->cb_buf) cudaFree(s->cb_buf);
     if (s->pkt) cudaFree(s->pkt);
     if (s->trace) cudaFree(s->trace);
