@@ -228,7 +228,7 @@ def main():
     # algorithmic bytes per launch of each streaming-kernel class
     class_bytes = {"two_loop_pass": (8 * h - 1) * V / (2 * h), "gram_rows": (2 * h + 1) * V, "combine": (2 * h + 2) * V,
                    "trial": 2 * V, "accept": 7 * V}
-    class_kernel = {"two_loop_pass": "k_two_loop_pass", "gram_rows": "k_gram", "combine": "k_combine",
+    class_kernel = {"two_loop_pass": "k_two_loop_pass", "gram_rows": "k_gram_tma2d" if M > 6 else "k_gram_tma", "combine": "k_combine",
                     "trial": "k_trial", "accept": "k_accept"}
     traffic_db = {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
