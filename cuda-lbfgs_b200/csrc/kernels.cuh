@@ -468,11 +468,9 @@ __device__ __forceinline__ void eval_item(const EvalCtx &c, long long j, long lo
     OBJ::eval(l, xt0, xt1, hl0, true, f0, g0);
     OBJ::eval(xt0, xt1, r, true, hr1, f1, g1);
     if (MODE == MODE_TRIAL) {
-        // the element-wise values above are bit-exact; the inner-product accumulations below carry no
-        // bitwise contract (their summation order already differs from the reference), so they are fused
         acc[0] += f0 + f1;
-        acc[1] = fma(g1, d2.y, fma(g0, d2.x, acc[1]));
-        acc[2] = fma(g1, g1, fma(g0, g0, acc[2]));
+        acc[1] += g0 * d2.x + g1 * d2.y;
+        acc[2] += g0 * g0 + g1 * g1;
         if (o.g_out) st2(o.g_out, j, make_double2(g0, g1));
     } else {
         const double s0 = xt0 - x2.x, s1 = xt1 - x2.y; // s = x_new - x (seq/lbfgs.cpp:177)
@@ -482,10 +480,10 @@ __device__ __forceinline__ void eval_item(const EvalCtx &c, long long j, long lo
         st2(o.s_out, j, make_double2(s0, s1));
         st2(o.y_out, j, make_double2(y0, y1));
         acc[0] += f0 + f1;
-        acc[1] = fma(g1, g1, fma(g0, g0, acc[1]));
-        acc[2] = fma(s1, y1, fma(s0, y0, acc[2]));
-        acc[3] = fma(y1, y1, fma(y0, y0, acc[3]));
-        acc[4] = fma(s1, g1, fma(s0, g0, acc[4]));
+        acc[1] += g0 * g0 + g1 * g1;
+        acc[2] += s0 * y0 + s1 * y1;
+        acc[3] += y0 * y0 + y1 * y1;
+        acc[4] += s0 * g0 + s1 * g1;
     }
 }
 
