@@ -409,3 +409,22 @@ def test_cuda_profile_matches_its_restatement(gpu, oracle, direction):
         k = info["iterations"]
         assert np.array_equal(tr[:k, 4], to[:k, 4]) and np.array_equal(tr[:k, 5], to[:k, 5]), tag
         assert np.max(np.abs(x - xo)) <= 1e-8 * max(np.max(np.abs(xo)), 1e-3), tag
+
+
+def test_error_paths_are_loud_and_leave_the_library_usable(gpu):
+    # out of device memory: a status and a message, not a crash
+    p = gpu.default_params("par", m=10)
+    with pytest.raises(gpu.LbfgsError, match="out of device memory"):
+        gpu.Solver("rosenbrock", 10 ** 12, p)
+    # iterate before set_x0
+    s = gpu.Solver("rosenbrock", 1000, p)
+    with pytest.raises(gpu.LbfgsError, match="set_x0"):
+        s.iterate(1)
+    s.destroy()
+    # the compact direction is limited to m <= 50
+    with pytest.raises(gpu.LbfgsError, match="compact direction supports"):
+        gpu.Solver("rosenbrock", 1000, gpu.default_params("par", m=60, direction="compact"))
+    # and the library still works afterwards
+    x, info, _ = gpu.solve("quadratic", gpu.x0_uniform(1000, -1000, 1000), "backtracking", "seq", tolerance=1e-8,
+                           max_iterations=100)
+    assert info["status"] == 0 and np.max(np.abs(x - 1.0)) < 1e-9
