@@ -74,7 +74,7 @@ EXPORTS = [
     "lbfgsb200_dot", "lbfgsb200_nrm2", "lbfgsb200_axpy", "lbfgsb200_scal", "lbfgsb200_eval_trial",
     "lbfgsb200_two_loop", "lbfgsb200_accept", "lbfgsb200_x0_uniform", "lbfgsb200_host_alloc",
     "lbfgsb200_host_free", "lbfgsb200_device_alloc", "lbfgsb200_device_free", "lbfgsb200_memcpy",
-    "lbfgsb200_set_device", "lbfgsb200_device_sync",
+    "lbfgsb200_set_device", "lbfgsb200_device_sync", "lbfgsb200_trim_memory", "lbfgsb200_mem_info",
 ]
 
 
@@ -150,6 +150,18 @@ def _check(rc, what):
         raise LbfgsError("%s: %s (%s)" % (what, L.lbfgsb200_strerror(rc).decode(),
                                           L.lbfgsb200_last_error().decode()))
     return rc
+
+
+def trim_memory():
+    """Hand the arenas cached by destroyed solvers back to the driver (lbfgsb200_trim_memory)."""
+    _check(lib().lbfgsb200_trim_memory(), "trim_memory")
+
+
+def mem_info():
+    """(free, total) device bytes; arenas cached by destroyed solvers count as used."""
+    f, t = C.c_size_t(), C.c_size_t()
+    _check(lib().lbfgsb200_mem_info(C.byref(f), C.byref(t)), "mem_info")
+    return f.value, t.value
 
 
 def default_params(flavor="seq", **overrides):

@@ -690,13 +690,6 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
 
     const size_t nvecs = 4 + 2 * (size_t)s->nslots;
     const size_t arena_bytes = nvecs * s->stride * sizeof(double);
-    cudaError_t e = cudaMalloc(&s->arena, arena_bytes);
-    if (e != cudaSuccess) {
-        set_error("cudaMalloc of %.2f GB for %zu vectors failed: %s", arena_bytes / 1e9, nvecs, cudaGetErrorString(e));
-        cudaGetLastError();
-        delete s;
-        return LBFGSB200_ERR_NOMEM;
-    }
 #define CREATE_TRY(expr)                                                                      \
     do {                                                                                      \
         cudaError_t e2_ = (expr);                                                             \
@@ -709,6 +702,26 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     CREATE_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaEventCreate(&s->ev0));
     CREATE_TRY(cudaEventCreate(&s->ev1));
+    // The arena ((2m+6) vectors, tens of GB) comes from the device's stream-ordered memory pool with the
+    // release threshold raised, so that destroying a solver and creating the next one of similar size
+    // re-uses the mapping instead of paying cudaMalloc/cudaFree of tens of GB (5-130 ms each way) again.
+    // lbfgsb200_trim_memory() hands the cached memory back to the driver.
+    {
+        int dev = 0;
+        cudaMemPool_t pool;
+        CREATE_TRY(cudaGetDevice(&dev));
+        CREATE_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = UINT64_MAX;
+        CREATE_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    cudaError_t e = cudaMallocAsync(&s->arena, arena_bytes, s->stream);
+    if (e != cudaSuccess) {
+        set_error("allocation of %.2f GB for %zu vectors failed: %s", arena_bytes / 1e9, nvecs, cudaGetErrorString(e));
+        cudaGetLastError();
+        s->arena = nullptr;
+        lbfgsb200_destroy(s);
+        return LBFGSB200_ERR_NOMEM;
+    }
     // Zero only what must be zero: the work vector w (d = 0 for the x0 evaluation) and the <= 31
     // pad doubles at the end of every row (the compact kernels read rows up to the padded length).
     // Everything else is written before it is read; clearing the whole arena would cost a full
@@ -833,7 +846,10 @@ void lbfgsb200_destroy(lbfgsb200_solver_t *s)
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int c = 0; c < LBFGSB200_PROFILE_CLASSES; ++c)
         for (cudaEvent_t e : s->prof_ev[c]) cudaEventDestroy(e);
-    if (s->arena) cudaFree(s->arena);
+    if (s->arena && s->stream) {
+        cudaFreeAsync(s->arena, s->stream); // back to the pool (see lbfgsb200_create)
+        cudaStreamSynchronize(s->stream);
+    }
     if (s->partials) cudaFree(s->partials);
     if (s->gram) cudaFree(s->gram);
     if (s->gram_maps) cudaFree(s->gram_maps);
@@ -1359,6 +1375,24 @@ void lbfgsb200_device_free(void *p) { if (p) cudaFree(p); }
 int lbfgsb200_memcpy(void *dst, const void *src, size_t bytes)
 {
     CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+    return 0;
+}
+int lbfgsb200_trim_memory(void)
+{
+    int dev = 0;
+    cudaMemPool_t pool;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+    CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
+    return 0;
+}
+int lbfgsb200_mem_info(size_t *free_bytes, size_t *total_bytes)
+{
+    size_t f = 0, t = 0;
+    CUDA_TRY(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
     return 0;
 }
 int lbfgsb200_set_device(int ordinal)

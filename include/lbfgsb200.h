@@ -234,6 +234,11 @@ void *lbfgsb200_device_alloc(size_t bytes);
 void lbfgsb200_device_free(void *p);
 int lbfgsb200_memcpy(void *dst, const void *src, size_t bytes);
 int lbfgsb200_set_device(int ordinal);
+/* Solver arenas are served from the device's stream-ordered memory pool and stay cached there after
+ * lbfgsb200_destroy() so that the next solver does not pay the allocation again; this releases them. */
+int lbfgsb200_trim_memory(void);
+/* free / total device memory as the driver sees it (cached arenas count as used) */
+int lbfgsb200_mem_info(size_t *free_bytes, size_t *total_bytes);
 int lbfgsb200_device_sync(void);
 
 #ifdef __cplusplus

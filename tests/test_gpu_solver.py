@@ -428,3 +428,29 @@ def test_error_paths_are_loud_and_leave_the_library_usable(gpu):
     x, info, _ = gpu.solve("quadratic", gpu.x0_uniform(1000, -1000, 1000), "backtracking", "seq", tolerance=1e-8,
                            max_iterations=100)
     assert info["status"] == 0 and np.max(np.abs(x - 1.0)) < 1e-9
+
+
+def test_arena_is_reused_from_the_pool_and_can_be_trimmed(gpu):
+    """Solver arenas come from the stream-ordered pool: a destroyed solver's memory is re-used by the next
+    create (no driver free in between) and lbfgsb200_trim_memory() gives it back."""
+    def free_bytes():
+        gpu.lib().lbfgsb200_device_sync()
+        return gpu.mem_info()[0]
+
+    gpu.trim_memory()
+    n = 1 << 24                                     # 22 vectors x 128 MiB
+    x0 = gpu.x0_uniform(n, -2, 2)
+    p = gpu.default_params("par", m=8, line_search="wolfe", max_iterations=5, tolerance=0.0)
+    before = free_bytes()
+    runs = []
+    for _ in range(2):
+        s = gpu.Solver("rosenbrock", n, p)
+        s.set_x0(x0)
+        s.iterate(5)
+        runs.append((s.x(), s.result()))
+        s.destroy()
+    held = before - free_bytes()
+    assert held >= 22 * n * 8                       # still cached after destroy
+    assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1]["f"] == runs[1][1]["f"]
+    gpu.trim_memory()
+    assert before - free_bytes() < 64 << 20         # handed back
