@@ -74,7 +74,7 @@ EXPORTS = [
     "lbfgsb200_dot", "lbfgsb200_nrm2", "lbfgsb200_axpy", "lbfgsb200_scal", "lbfgsb200_eval_trial",
     "lbfgsb200_two_loop", "lbfgsb200_accept", "lbfgsb200_x0_uniform", "lbfgsb200_host_alloc",
     "lbfgsb200_host_free", "lbfgsb200_device_alloc", "lbfgsb200_device_free", "lbfgsb200_memcpy",
-    "lbfgsb200_set_device", "lbfgsb200_device_sync", "lbfgsb200_trim_memory", "lbfgsb200_mem_info",
+    "lbfgsb200_set_device", "lbfgsb200_device_sync", "lbfgsb200_trim_memory", "lbfgsb200_mem_info", "lbfgsb200_debug_timeline",
 ]
 
 

@@ -455,7 +455,9 @@ __global__ void __launch_bounds__(kScalarThreads) k_gram_finalize(DevState *st, 
 // products of the recursion are warp-parallel (lane-strided partial sums + the fixed shuffle tree:
 // deterministic), the O(1) updates in between are done by lane 0 of warp 0.
 // rows: the finalised 3 x J inner products of pass A (already summed over ranks on multi-GPU).
-__device__ void compact_recursion(DevState *st, const double *rows)
+// Gs: J*J doubles of shared memory; the window Gram matrix is staged there so that the 2h dependent
+// steps of the recursion run at shared-memory latency (in HBM they cost ~1.4 us each: 29 us at m = 10).
+__device__ void compact_recursion(DevState *st, const double *rows, double *Gs)
 {
     const int h = st->h, J = 2 * h + 1, ns = st->nslots, NB = 2 * ns + 1;
     const bool seq = st->profile == LBFGSB200_PROFILE_SEQ;
@@ -488,16 +490,21 @@ __device__ void compact_recursion(DevState *st, const double *rows)
         G[b * NB + ig] = G[ig * NB + b];
     }
     __syncthreads();
+    // window order: Gs[a][b] = <basis column a, basis column b>
+    for (int idx = threadIdx.x; idx < J * J; idx += kScalarThreads) {
+        const int a = idx / J, b = idx - a * J;
+        Gs[idx] = G[bi[a] * NB + bi[b]];
+    }
+    __syncthreads();
     if (threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
     int bad = 0;
     // first loop, newest -> oldest (seq/lbfgs.cpp:100-114)
     for (int p = h - 1; p >= 0; --p) {
-        const int bs = bi[p], by = bi[h + p];
-        const double rho = 1.0 / G[by * NB + bs];
+        const double rho = 1.0 / Gs[(h + p) * J + p];
         if (seq && !isfinite(rho)) bad = 1;
         double sq = 0.0;
-        for (int j = lane; j < J; j += 32) sq += delta[j] * G[bs * NB + bi[j]];
+        for (int j = lane; j < J; j += 32) sq += delta[j] * Gs[p * J + j];
         sq = warp_sum(sq);
         const double a = st->skip[slot_of(*st, p)] ? 0.0 : rho * sq;
         __syncwarp();
@@ -507,21 +514,20 @@ __device__ void compact_recursion(DevState *st, const double *rows)
         }
         __syncwarp();
     }
-    double gamma = G[is_new * NB + iy_new] / G[iy_new * NB + iy_new]; // :117
+    const double ys = Gs[(h - 1) * J + 2 * h - 1], yy = Gs[(2 * h - 1) * J + 2 * h - 1];
+    double gamma = ys / yy; // :117
     if (seq) {
         if (gamma <= 0 || !isfinite(gamma)) bad = 1;
     } else {
-        const double ys = G[is_new * NB + iy_new], yy = G[iy_new * NB + iy_new];
         gamma = (yy > 0 && ys > 1e-10) ? ys / yy : 1.0; // par/L-BFGS.cu:246-255
     }
     for (int j = lane; j < J; j += 32) delta[j] = delta[j] * gamma; // r = gamma q
     __syncwarp();
     // second loop, oldest -> newest (:133-141)
     for (int p = 0; p < h; ++p) {
-        const int bs = bi[p], by = bi[h + p];
-        const double rho = 1.0 / G[by * NB + bs];
+        const double rho = 1.0 / Gs[(h + p) * J + p];
         double yr = 0.0;
-        for (int j = lane; j < J; j += 32) yr += delta[j] * G[by * NB + bi[j]];
+        for (int j = lane; j < J; j += 32) yr += delta[j] * Gs[(h + p) * J + j];
         yr = warp_sum(yr);
         const double beta = rho * yr;
         __syncwarp();
@@ -539,6 +545,33 @@ __device__ void compact_recursion(DevState *st, const double *rows)
             st->vec_streams += 2.0;
         }
     }
+}
+
+// In-kernel version of k_gram_finalize for the 1-CTA scalar kernel: warp w sums rows w, w+8, ... of the
+// per-CTA partials (lane-strided partial sums, then the fixed shuffle tree: deterministic), four rows
+// in flight per warp.  out: 3 x (2h+1) sums followed by zeros up to `count`.
+__device__ __forceinline__ void gram_rows_from_partials(const double *__restrict__ partials, int nparts, int nrows,
+                                                        int count, double *out /* shared */)
+{
+    constexpr int W = kScalarThreads / 32, R = 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q0 = warp; q0 < nrows; q0 += W * R) {
+        double v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            v[r] = 0.0;
+            const int q = q0 + r * W;
+            if (q < nrows)
+                for (int i = lane; i < nparts; i += 32) v[r] += partials[(size_t)q * nparts + i];
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double t = warp_sum(v[r]);
+            if (lane == 0 && q0 + r * W < nrows) out[q0 + r * W] = t;
+        }
+    }
+    for (int q = nrows + threadIdx.x; q < count; q += kScalarThreads) out[q] = 0.0;
+    __syncthreads();
 }
 
 // pass B.  w = d = -(sum_j delta_j b_j), accumulated in window-column order; partial of g.d.

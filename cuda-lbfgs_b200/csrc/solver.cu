@@ -107,6 +107,7 @@ struct lbfgsb200_solver {
     double *partials = nullptr; // [kMaxQ][grid]
     double *pkt = nullptr;      // send [kPacket] + recv [nranks][kPacket]
     double *trace = nullptr;
+    unsigned long long *timeline = nullptr; // LBFGSB200_TIMELINE diagnostic (DevState::tl)
     size_t trace_rows = 0;
     DevState *d_st = nullptr;
     Ctrl *h_ctrl = nullptr;     // pinned
@@ -210,17 +211,21 @@ static int launch_direction(lbfgsb200_solver *s)
                 else if (cwg <= 6) k_gram<6><<<grid, kThreads, smem, s->stream>>>(s->d_st, s->gram_T, s->gram_NS, G);
                 else k_gram<kMaxCW><<<grid, kThreads, smem, s->stream>>>(s->d_st, s->gram_T, s->gram_NS, G);
             }
-            k_gram_finalize<<<3 * J, kScalarThreads, 0, s->stream>>>(s->d_st, s->grid_gram);
-            s->launches += 2;
+            s->launches += 1;
         }
         const bool multi = s->comm && s->comm->nranks > 1;
         const bool p2p = multi && s->comm->p2p;
         if (multi && !p2p) {
+            // NCCL path: the rows must be in HBM for the all-gather (otherwise the scalar kernel sums them itself)
+            k_gram_finalize<<<3 * J, kScalarThreads, 0, s->stream>>>(s->d_st, s->grid_gram);
+            s->launches += 1;
             const int cnt = 3 * (2 * m + 1);
             double *rows = s->h_snapshot.gram_rows;
             LB_TRY(comm_allgather(s->comm, rows, s->h_snapshot.gram_recv, cnt, s->stream));
         }
-        k_scalar<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, OP_COMPACT, 0, p2p ? 2 : (multi ? 1 : 0), PACK_NONE, 0);
+        // dynamic shared memory: the (2h+1)^2 window Gram matrix of the coefficient recursion
+        k_scalar<<<1, kScalarThreads, sizeof(double) * (size_t)J * J, s->stream>>>(s->d_st, OP_COMPACT, 0, p2p ? 2 : (multi ? 1 : 0),
+                                                                                   PACK_NONE, s->grid_gram);
         s->launches += 1;
         {
             ClassTimer t(s, KC_COMBINE);
@@ -757,6 +762,8 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
             lbfgsb200_destroy(s);
             return LBFGSB200_ERR_INVALID;
         }
+        CREATE_TRY(cudaFuncSetAttribute((const void *)k_scalar, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(sizeof(double) * kMaxCols * kMaxCols)));
         const void *variants[] = {(const void *)k_gram<3>, (const void *)k_gram<6>, (const void *)k_gram<kMaxCW>,
                                   (const void *)k_gram_tma<7>, (const void *)k_gram_tma<kMaxCW>,
                                   (const void *)k_gram_tma2d<7>, (const void *)k_gram_tma2d<kMaxCW>};
@@ -829,6 +836,13 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     st.lsp.bt_tol = params->backtracking_tol;
     st.lsp.wolfe_min = params->wolfe_min;
     st.status = LBFGSB200_RUNNING;
+    if (const char *et = getenv("LBFGSB200_TIMELINE")) {
+        st.tl_cap = atoi(et);
+        if (st.tl_cap > 0) {
+            CREATE_TRY(cudaMalloc(&s->timeline, sizeof(unsigned long long) * 3 * (size_t)st.tl_cap));
+            st.tl = s->timeline;
+        }
+    }
     if (s->gram && s->gram_tma == 2) {
         int rc_maps = build_gram_maps(s, st);
         if (rc_maps < 0) { lbfgsb200_destroy(s); return rc_maps; }
@@ -856,6 +870,7 @@ void lbfgsb200_destroy(lbfgsb200_solver_t *s)
     if (s->cb_buf) cudaFree(s->cb_buf);
     if (s->pkt) cudaFree(s->pkt);
     if (s->trace) cudaFree(s->trace);
+    if (s->timeline) cudaFree(s->timeline);
     if (s->d_st) cudaFree(s->d_st);
     if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
@@ -990,6 +1005,7 @@ int lbfgsb200_checkpoint_load(lbfgsb200_solver_t *s, const char *path)
     st.gram = cur.gram; st.gram_rows = cur.gram_rows; st.gram_recv = cur.gram_recv; st.delta = cur.delta;
     st.mail = cur.mail; st.peers = cur.peers; st.p2p = cur.p2p; st.p2p_timeout_ns = cur.p2p_timeout_ns;
     st.cond_outer = cur.cond_outer; st.cond_inner = cur.cond_inner; st.use_graph = cur.use_graph;
+    st.tl = cur.tl; st.tl_cap = cur.tl_cap; st.tl_n = cur.tl_n;
     st.max_iterations = cur.max_iterations; st.tolerance = cur.tolerance; st.lsp = cur.lsp; // the new handle's limits apply
     if (st.status != LBFGSB200_CONVERGED && st.status != LBFGSB200_LS_FAILED && st.k < st.max_iterations) {
         st.status = LBFGSB200_RUNNING; // a run that only ran out of iterations may continue
@@ -1020,6 +1036,7 @@ int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local)
     st.ctrl.k = 0;
     st.status = LBFGSB200_RUNNING;
     st.use_graph = 0; // re-armed per run by do_iterate
+    st.tl_n = 0;
     st.xL = st.xR = st.dL = st.dR = st.gL = st.gR = 0.0;
     CUDA_TRY(cudaMemcpyAsync(s->d_st, &st, sizeof st, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream)); // st is a stack object
@@ -1376,6 +1393,19 @@ int lbfgsb200_memcpy(void *dst, const void *src, size_t bytes)
 {
     CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
     return 0;
+}
+long lbfgsb200_debug_timeline(lbfgsb200_solver_t *s, unsigned long long *rows, size_t cap_rows, int reset)
+{
+    if (!s || !s->timeline) { set_error("debug_timeline: create the solver with LBFGSB200_TIMELINE=<rows> set"); return LBFGSB200_ERR_INVALID; }
+    LB_TRY(snapshot(s));
+    size_t nrows = (size_t)s->h_snapshot.tl_n;
+    if (nrows > cap_rows) nrows = cap_rows;
+    if (rows && nrows) CUDA_TRY(cudaMemcpy(rows, s->timeline, sizeof(unsigned long long) * 3 * nrows, cudaMemcpyDeviceToHost));
+    if (reset) {
+        const int zero = 0;
+        CUDA_TRY(cudaMemcpy((char *)s->d_st + offsetof(DevState, tl_n), &zero, sizeof zero, cudaMemcpyHostToDevice));
+    }
+    return (long)nrows;
 }
 int lbfgsb200_trim_memory(void)
 {

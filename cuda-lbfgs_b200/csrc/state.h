@@ -124,6 +124,11 @@ struct DevState {
     double *gram_recv; // multi-GPU: all-gathered gram_rows, [nranks][gram_count]
     int gram_count;    // doubles per rank in that exchange: 3 * (2m+1)
     double *delta;     // direction coefficients by window column
+
+    // ---- diagnostic timeline (LBFGSB200_TIMELINE=rows): (op, %globaltimer at entry, at exit) of every
+    //      scalar kernel, so that the gaps between the vector kernels can be read off the device ----
+    unsigned long long *tl;
+    int tl_cap, tl_n;
 };
 
 __host__ __device__ inline int slot_of(const DevState &st, int pos)

@@ -237,6 +237,10 @@ int lbfgsb200_set_device(int ordinal);
 /* Solver arenas are served from the device's stream-ordered memory pool and stay cached there after
  * lbfgsb200_destroy() so that the next solver does not pay the allocation again; this releases them. */
 int lbfgsb200_trim_memory(void);
+/* Diagnostic: with LBFGSB200_TIMELINE=<rows> in the environment at create time every scalar kernel records
+ * (op, %globaltimer ns at entry, at exit); this copies up to cap_rows rows of 3 u64 out and returns the count.
+ * The gaps between rows are the vector kernels plus launch latency (benchmarks/timeline.py). */
+long lbfgsb200_debug_timeline(lbfgsb200_solver_t *s, unsigned long long *rows, size_t cap_rows, int reset);
 /* free / total device memory as the driver sees it (cached arenas count as used) */
 int lbfgsb200_mem_info(size_t *free_bytes, size_t *total_bytes);
 int lbfgsb200_device_sync(void);
