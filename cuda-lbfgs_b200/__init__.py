@@ -29,7 +29,7 @@ LIB_PATH = build_module.LIB
 
 OBJ = {"quadratic": 0, "rosenbrock": 1, "tridiag": 2}
 LS = {"backtracking": 0, "interpolation": 1, "wolfe": 2, "backtracking_wolfe": 3}
-FLAVOR = {"seq": 0, "par": 1}
+FLAVOR = {"seq": 0, "par": 1, "par_inlined": 2}
 PROFILE = {"seq": 0, "cuda": 1}
 DIRECTION = {"two_loop": 0, "compact": 1}
 STATUS = {0: "converged", 1: "max_iter", 2: "ls_failed", 3: "running"}

@@ -20,7 +20,12 @@
 namespace lb {
 
 enum { LS_BACKTRACKING = 0, LS_INTERPOLATION = 1, LS_WOLFE = 2, LS_BACKTRACKING_WOLFE = 3 };
-enum { FLAVOR_SEQ = 0, FLAVOR_PAR = 1 };
+// FLAVOR_SEQ: seq/line_search.cpp + seq/config.h.  FLAVOR_PAR: par/line_search.cpp + par/constants.h (what
+// par/L-BFGS.cu calls).  FLAVOR_PAR_INLINED: the searches as they are inlined in the other CUDA solvers
+// (par/L-BFGS-Wolfe.cu:260-349, par/L-BFGS-Interpolation.cu:259-342, par/L-BFGS-Backtracking.cu:292-341,
+// par/L-BFGS-Backtracking_Wolfe.cu:262-397), which differ from par/line_search.cpp in a few places --
+// see ls_begin(..., f0) and the FLAVOR_PAR_INLINED branches of ls_step().
+enum { FLAVOR_SEQ = 0, FLAVOR_PAR = 1, FLAVOR_PAR_INLINED = 2 };
 
 struct LsParams {
     int kind;   // LS_*
@@ -38,6 +43,10 @@ struct LsState {
     double alpha_prev, f_prev;
     // wolfe / bisection wolfe
     double lo, hi, f_lo, dphi_lo;
+    // bookkeeping of the last evaluated trial (FLAVOR_PAR_INLINED: the reference's x_host)
+    double alpha_last, f_last;
+    int success;   // the search ended by accepting an evaluated trial
+    int stale;     // it returned a step that differs from the last evaluated trial
 };
 
 // seq/line_search.cpp:8-12 == par/line_search.cpp:10-15
@@ -84,7 +93,7 @@ LB_HD double safe_cubic_interpolate(double alpha0, double alpha1, double phi0, d
 LB_HD double ls_interp(const LsParams &p, double a0, double a1, double p0, double dp0, double p1,
                        double dp1)
 {
-    return p.flavor == FLAVOR_PAR ? safe_cubic_interpolate(a0, a1, p0, dp0, p1, dp1)
+    return p.flavor != FLAVOR_SEQ ? safe_cubic_interpolate(a0, a1, p0, dp0, p1, dp1)
                                   : cubic_interpolate(a0, a1, p0, dp0, p1, dp1);
 }
 
@@ -108,12 +117,29 @@ LB_HD int ls_begin(const LsParams &p, LsState &s, double f_x, double gd)
     s.hi = (p.kind == LS_BACKTRACKING_WOLFE) ? 1.7976931348623157e308 : INFINITY;
     s.f_lo = f_x;
     s.dphi_lo = gd;
+    s.success = 0;
     return 1;
 }
 
-// Consume the evaluation at s.alpha.  Returns 1: evaluate the new s.alpha; 0: finished,
-// s.alpha is the step the search returns.
-LB_HD int ls_step(const LsParams &p, LsState &s, double f_new, double dphi_new)
+// Start a search inside the solver loop: f_cur = f(x_k), f0 = f(x_0).  For FLAVOR_SEQ / FLAVOR_PAR this is
+// ls_begin(p, s, f_cur, gd).  The inlined CUDA searches (FLAVOR_PAR_INLINED) instead
+//  * take "f(x_k)" from f(x_host), where x_host still holds the LAST TRIAL POINT the previous search evaluated
+//    (par/L-BFGS-Wolfe.cu:270 with :282-288, par/L-BFGS-Interpolation.cu:267 with :279-285,
+//    par/L-BFGS-Backtracking_Wolfe.cu:266 with :297-303): equal to f(x_k) only when that search returned
+//    the step it evaluated last; the inlined backtracking re-reads d_x and has no such dependence
+//    (par/L-BFGS-Backtracking.cu:308-312);
+//  * seed the Wolfe bracket's f_lo with f(x_0) in EVERY iteration (par/L-BFGS-Wolfe.cu:267, initial_f :172).
+// s must still hold the state the previous search left behind (all zero before the first one).
+LB_HD int ls_begin(const LsParams &p, LsState &s, double f_cur, double gd, double f0)
+{
+    double f_x = f_cur;
+    if (p.flavor == FLAVOR_PAR_INLINED && p.kind != LS_BACKTRACKING && s.stale) f_x = s.f_last;
+    ls_begin(p, s, f_x, gd);
+    if (p.flavor == FLAVOR_PAR_INLINED && p.kind == LS_WOLFE) s.f_lo = f0;
+    return 1;
+}
+
+LB_HD int ls_step_core(const LsParams &p, LsState &s, double f_new, double dphi_new)
 {
     const double alpha = s.alpha;
     const int iter = s.trials; // index of the trial just evaluated
@@ -121,6 +147,14 @@ LB_HD int ls_step(const LsParams &p, LsState &s, double f_new, double dphi_new)
 
     switch (p.kind) {
     case LS_BACKTRACKING: {
+        if (p.flavor == FLAVOR_PAR_INLINED) {
+            // par/L-BFGS-Backtracking.cu:314-341: the textbook Armijo test, and 0.5 once the step is tiny
+            if (f_new <= s.f_x + p.c1 * alpha * s.gd) { s.success = 1; return 0; }
+            const double a = alpha * p.shrink;
+            s.alpha = a;
+            if (a < p.bt_tol) { s.alpha = 0.5; return 0; }
+            return 1;
+        }
         // seq/line_search.cpp:23-27.  The reference's test is
         //   f(x) - f(x+alpha d) < C1*alpha*(g.d)   (continue shrinking while true)
         if (s.f_x - f_new < p.c1 * alpha * s.gd) {
@@ -137,8 +171,15 @@ LB_HD int ls_step(const LsParams &p, LsState &s, double f_new, double dphi_new)
     }
     case LS_INTERPOLATION: {
         // seq/line_search.cpp:73-118
-        if (f_new <= s.f_x + p.c1 * alpha * s.gd) return 0;  // :83-85 (no floor on this path)
-        if (alpha < p.wolfe_min) { s.alpha = p.wolfe_min; return 0; } // :87-89
+        // the inlined copy applies its "alpha < 1e-4 => 0.5" AFTER the loop, i.e. to every exit
+        // (par/L-BFGS-Interpolation.cu:338-341); par/line_search.cpp only to the exhausted one (:223-226)
+        const bool inl = p.flavor == FLAVOR_PAR_INLINED;
+        if (f_new <= s.f_x + p.c1 * alpha * s.gd) { // :83-85 (no floor on this path)
+            s.success = 1;
+            if (inl && alpha < 1e-4) s.alpha = 0.5;
+            return 0;
+        }
+        if (alpha < p.wolfe_min) { s.alpha = inl ? 0.5 : p.wolfe_min; return 0; } // :87-89
         double a;
         if (s.alpha_prev > 0) {
             double delta_alpha = alpha - s.alpha_prev;
@@ -157,7 +198,7 @@ LB_HD int ls_step(const LsParams &p, LsState &s, double f_new, double dphi_new)
         s.f_prev = f_new;
         s.alpha = a;
         if (s.trials < p.max_trials) return 1;
-        s.alpha = ls_par_floor(p, a); // :120 / par :223-227
+        s.alpha = (inl && a < 1e-4) ? 0.5 : ls_par_floor(p, a); // :120 / par :223-227
         return 0;
     }
     case LS_WOLFE: {
@@ -170,7 +211,7 @@ LB_HD int ls_step(const LsParams &p, LsState &s, double f_new, double dphi_new)
             s.alpha = a; // `continue`: skips the alpha < MIN test
             return s.trials < p.max_trials ? 1 : 0;
         }
-        if (fabs(dphi_new) <= -p.c2 * s.gd) return 0; // strong Wolfe: accept alpha
+        if (fabs(dphi_new) <= -p.c2 * s.gd) { s.success = 1; return 0; } // strong Wolfe: accept alpha
         if (dphi_new >= 0) {
             s.hi = alpha;
             a = ls_interp(p, s.lo, s.hi, s.f_lo, s.dphi_lo, f_new, dphi_new);
@@ -194,7 +235,7 @@ LB_HD int ls_step(const LsParams &p, LsState &s, double f_new, double dphi_new)
             double a = alpha;
             if (f_new > s.f_x + p.c1 * alpha * s.gd) a = alpha * p.shrink;
             else if (dphi_new < p.c2 * s.gd) a = alpha * 1.1;
-            else return 0;
+            else { s.success = 1; return 0; }
             s.alpha = a;
             if (a < p.bt_tol) return 0;
             return s.trials < p.max_trials * 5000 ? 1 : 0;
@@ -202,7 +243,7 @@ LB_HD int ls_step(const LsParams &p, LsState &s, double f_new, double dphi_new)
         // par/line_search.cpp:52-153: bisection, local constants C1=1e-4, C2=0.9, TOL=1e-10
         const double DMAX = 1.7976931348623157e308;
         if (f_new <= s.f_x + 1e-4 * alpha * s.gd) {
-            if (dphi_new >= 0.9 * s.gd) return 0;
+            if (dphi_new >= 0.9 * s.gd) { s.success = 1; return 0; }
             s.lo = alpha;
         } else {
             s.hi = alpha;
@@ -211,10 +252,26 @@ LB_HD int ls_step(const LsParams &p, LsState &s, double f_new, double dphi_new)
         if (s.hi < DMAX) a = (s.lo + s.hi) / 2.0;
         else a = 2.0 * s.lo;
         s.alpha = a;
-        if (a < 1e-10) return 0;
+        if (a < 1e-10) {
+            // the inlined copy steps to exactly TOL and evaluates f and the gradient there
+            // (par/L-BFGS-Backtracking_Wolfe.cu:371-396), so x_host ends up AT the returned step
+            if (p.flavor == FLAVOR_PAR_INLINED) { s.alpha = 1e-10; s.alpha_last = 1e-10; }
+            return 0;
+        }
         return s.trials < 20 ? 1 : 0;
     }
     }
+}
+
+// Consume the evaluation at s.alpha.  Returns 1: evaluate the new s.alpha; 0: finished,
+// s.alpha is the step the search returns.
+LB_HD int ls_step(const LsParams &p, LsState &s, double f_new, double dphi_new)
+{
+    s.alpha_last = s.alpha;
+    s.f_last = f_new;
+    const int cont = ls_step_core(p, s, f_new, dphi_new);
+    if (!cont) s.stale = (s.alpha != s.alpha_last);
+    return cont;
 }
 
 } // namespace lb

@@ -310,7 +310,7 @@ __device__ void scalar_logic(DevState *st, int op, int p, const double *r)
             st->dL = -st->gL;
             st->dR = -st->gR;
         }
-        ls_begin(st->lsp, st->ls, st->f, st->gd);
+        ls_begin(st->lsp, st->ls, st->f, st->gd, st->f0);
         st->ctrl.ls_active = 1;
         break;
     }
@@ -321,7 +321,10 @@ __device__ void scalar_logic(DevState *st, int op, int p, const double *r)
         const int cont = ls_step(st->lsp, st->ls, r[0], r[1]);
         if (!cont) {
             st->ctrl.ls_active = 0;
-            if (st->ls.alpha < 1e-10) { // seq/lbfgs.cpp:164-168: give up, keep the OLD x
+            // seq/lbfgs.cpp:164-168, par/L-BFGS.cu:295: a step below 1e-10 => give up, keep the OLD x.  The inlined
+            // searches give up only if they also did not succeed (par/L-BFGS-Wolfe.cu:353), backtracking never.
+            const bool inl = st->lsp.flavor == FLAVOR_PAR_INLINED;
+            if (st->ls.alpha < 1e-10 && !(inl && (st->ls.success || st->lsp.kind == LS_BACKTRACKING))) {
                 st->status = LBFGSB200_LS_FAILED;
                 st->ctrl.done = 1;
             }

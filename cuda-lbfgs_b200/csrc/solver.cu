@@ -527,10 +527,10 @@ int lbfgsb200_params_default(lbfgsb200_params_t *p, int flavor)
     p->profile = LBFGSB200_PROFILE_SEQ;
     p->direction = LBFGSB200_DIR_TWO_LOOP;
     p->c1 = 1e-4;                                         // seq/config.h:5, par/constants.h:5
-    p->c2 = (flavor == LBFGSB200_FLAVOR_PAR) ? 0.7 : 0.9; // par/constants.h:6 / seq/config.h:6
+    p->c2 = (flavor != LBFGSB200_FLAVOR_SEQ) ? 0.7 : 0.9; // par/constants.h:6 / seq/config.h:6
     p->step0 = 1.0;                                       // INITIAL_STEP_SIZE
     p->shrink = 0.5;                                      // BACKTRACKING_ALPHA
-    p->backtracking_tol = 1e-8;                           // BACKTRACKING_TOL
+    p->backtracking_tol = (flavor == LBFGSB200_FLAVOR_PAR_INLINED) ? 1e-10 : 1e-8; // BACKTRACKING_TOL (par/L-BFGS-Backtracking.cu:155)
     p->wolfe_min = 1e-10;                                 // WOLFE_INTERP_MIN
     p->ls_max_trials = 20;
     p->use_graph = 0;
@@ -600,7 +600,7 @@ static int check_params(const lbfgsb200_params_t *p)
         set_error("Unknown line search method: %d", p->line_search);
         return LBFGSB200_ERR_INVALID;
     }
-    if (p->flavor < 0 || p->flavor > 1 || p->profile < 0 || p->profile > 1 || p->direction < 0 ||
+    if (p->flavor < 0 || p->flavor > 2 || p->profile < 0 || p->profile > 1 || p->direction < 0 ||
         p->direction > 1) {
         set_error("bad flavor/profile/direction");
         return LBFGSB200_ERR_INVALID;
@@ -1036,6 +1036,7 @@ int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local)
     st.ctrl.k = 0;
     st.status = LBFGSB200_RUNNING;
     st.use_graph = 0; // re-armed per run by do_iterate
+    memset(&st.ls, 0, sizeof st.ls); // FLAVOR_PAR_INLINED carries state from one search to the next
     st.tl_n = 0;
     st.xL = st.xR = st.dL = st.dR = st.gL = st.gR = 0.0;
     CUDA_TRY(cudaMemcpyAsync(s->d_st, &st, sizeof st, cudaMemcpyHostToDevice, s->stream));

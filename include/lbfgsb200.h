@@ -39,8 +39,14 @@ typedef enum {
 
 /* which tree's line-search code and constants are followed:
  * SEQ = seq/line_search.cpp + seq/config.h (C2=0.9, cubicInterpolate),
- * PAR = par/line_search.cpp + par/constants.h (C2=0.7, safeCubicInterpolate, 0.5 floor) */
-typedef enum { LBFGSB200_FLAVOR_SEQ = 0, LBFGSB200_FLAVOR_PAR = 1 } lbfgsb200_flavor_t;
+ * PAR = par/line_search.cpp + par/constants.h (C2=0.7, safeCubicInterpolate, 0.5 floor) -- what par/L-BFGS.cu calls,
+ * PAR_INLINED = the copies of those searches inlined in the other CUDA solvers (par/L-BFGS-Wolfe.cu:260-349,
+ *   par/L-BFGS-Interpolation.cu:259-342, par/L-BFGS-Backtracking.cu:292-341, par/L-BFGS-Backtracking_Wolfe.cu:262-397):
+ *   as PAR, except that f(x_k) is taken at the last trial point the previous search evaluated, the Wolfe bracket's
+ *   f_lo starts at f(x_0) in every iteration, backtracking uses the textbook Armijo test with TOL=1e-10, and
+ *   interpolation applies its 0.5 floor to every exit.  Pinned against those programs run on a B200
+ *   (tests/golden/cuda_reference_traces.json). */
+typedef enum { LBFGSB200_FLAVOR_SEQ = 0, LBFGSB200_FLAVOR_PAR = 1, LBFGSB200_FLAVOR_PAR_INLINED = 2 } lbfgsb200_flavor_t;
 
 /* outer-loop semantics:
  * SEQ  = seq/lbfgs.cpp:72-199 (test ||g||<tol before the step, store a pair only if s.y>0,

@@ -32,7 +32,7 @@
 
 namespace lbfgsb200 {
 struct CompatOptions {
-    int flavor = -1;          // -1: LBFGS -> SEQ tree, LBFGS_CUDA -> PAR tree
+    int flavor = -1;          // -1: LBFGS -> SEQ tree, LBFGS_CUDA(method) -> PAR tree, LBFGS_CUDA() -> inlined searches
     int profile = -1;         // -1: LBFGS -> SEQ outer loop, LBFGS_CUDA -> CUDA outer loop
     int direction = LBFGSB200_DIR_TWO_LOOP;
     int use_graph = 0;
@@ -138,7 +138,7 @@ namespace detail {
 inline std::vector<double> run(const std::function<double(std::vector<double>)> &f,
                                const std::function<std::vector<double>(std::vector<double>)> &grad,
                                const std::vector<double> &x0, const std::string &method, int max_iterations,
-                               int m, double tolerance, bool verbose, bool cuda_entry)
+                               int m, double tolerance, bool verbose, bool cuda_entry, bool inlined_entry = false)
 {
     CompatOptions &o = compat_options();
     int ls;
@@ -153,7 +153,8 @@ inline std::vector<double> run(const std::function<double(std::vector<double>)> 
             "lbfgsb200: the objective is not one of the built-in device objectives (quadratic, rosenbrock, "
             "tridiagonal quadratic); host callbacks cannot run on the GPU and there is no CPU fallback");
     lbfgsb200_params_t p;
-    const int flavor = o.flavor >= 0 ? o.flavor : (cuda_entry ? LBFGSB200_FLAVOR_PAR : LBFGSB200_FLAVOR_SEQ);
+    const int flavor = o.flavor >= 0 ? o.flavor
+                     : (inlined_entry ? LBFGSB200_FLAVOR_PAR_INLINED : cuda_entry ? LBFGSB200_FLAVOR_PAR : LBFGSB200_FLAVOR_SEQ);
     lbfgsb200_params_default(&p, flavor);
     p.profile = o.profile >= 0 ? o.profile : (cuda_entry ? LBFGSB200_PROFILE_CUDA : LBFGSB200_PROFILE_SEQ);
     p.direction = o.direction;
@@ -217,8 +218,9 @@ std::vector<double> LBFGS_CUDA(const std::function<double(std::vector<double>)> 
                                const std::vector<double> x0, const int max_iterations, const int m,
                                const double tolerance)
 {
+    // this signature belongs to the solvers with an inlined search (par/L-BFGS-Wolfe.cu:105-111, ...)
     return lbfgsb200::detail::run(f, grad, x0, lbfgsb200::compat_options().cuda_default_line_search, max_iterations,
-                                  m, tolerance, false, true);
+                                  m, tolerance, false, true, true);
 }
 
 #endif // LBFGSB200_COMPAT_IMPLEMENTATION

@@ -198,7 +198,7 @@ static const double INITIAL_STEP_SIZE = 1.0;
 static const double BACKTRACKING_ALPHA = 0.5;
 static const double BACKTRACKING_TOL = 1e-8;
 static const double WOLFE_INTERP_MIN = 1e-10;
-static double c2_of(int flavor) { return flavor == ORACLE_FLAVOR_PAR ? 0.7 : 0.9; }
+static double c2_of(int flavor) { return flavor != ORACLE_FLAVOR_SEQ ? 0.7 : 0.9; }
 
 /* seq/line_search.cpp:19-30 ; par/line_search.cpp:25-43 (adds the 0.5 floor) */
 static double ls_backtracking(phi_t *p, int flavor)
@@ -360,6 +360,184 @@ static double run_ls(int ls, int flavor, phi_t *p)
     }
 }
 
+
+/* ------------------------------------------------------------------ */
+/* the searches as INLINED in the CUDA solvers (ORACLE_FLAVOR_PAR_INLINED) */
+/* ------------------------------------------------------------------ */
+/* What the solver loop carries from one search to the next: the reference keeps evaluating trial
+ * points into the host vector x_host and, at the top of the next iteration, takes "f(x_k)" as
+ * f(x_host) (par/L-BFGS-Wolfe.cu:270, par/L-BFGS-Interpolation.cu:267,
+ * par/L-BFGS-Backtracking_Wolfe.cu:266).  f_xhost is that value; f_initial is f(x0)
+ * (par/L-BFGS-Wolfe.cu:172). */
+typedef struct {
+    double f_xhost, f_initial;
+    int success;
+} inl_t;
+
+static double inl_f_at(phi_t *p, inl_t *q, double alpha)
+{
+    q->f_xhost = p->f_at(p, alpha); /* D2H of the trial point into x_host, then f(x_host) */
+    return q->f_xhost;
+}
+
+/* par/L-BFGS-Wolfe.cu:260-349 */
+static double ls_inl_wolfe(phi_t *p, inl_t *q)
+{
+    const double C2 = 0.7; /* par/constants.h:6 */
+    const double grad_dot_d = p->gd;
+    double alpha_current = INITIAL_STEP_SIZE;
+    double alpha_lo = 0.0;
+    double alpha_hi = INFINITY;
+    double f_lo = q->f_initial; /* :267 -- f(x0) in every iteration */
+    double dphi_lo = grad_dot_d;
+    const double f_x = q->f_xhost; /* :270 */
+    p->nf++;
+    q->success = 0;
+    for (int iter = 0; iter < 20; ++iter) {
+        const double f_new = inl_f_at(p, q, alpha_current);
+        if (f_new > f_x + C1 * alpha_current * grad_dot_d || (f_new >= f_lo && iter > 0)) {
+            alpha_hi = alpha_current;
+            alpha_current = oracle_safe_cubic(alpha_lo, alpha_hi, f_lo, dphi_lo, f_new,
+                                              (f_new - f_x - grad_dot_d * alpha_current) /
+                                                  (alpha_current * alpha_current));
+            continue;
+        }
+        const double dphi_new = p->df_at(p, alpha_current);
+        if (fabs(dphi_new) <= -C2 * grad_dot_d) {
+            q->success = 1;
+            break;
+        }
+        if (dphi_new >= 0) {
+            alpha_hi = alpha_current;
+            alpha_current = oracle_safe_cubic(alpha_lo, alpha_hi, f_lo, dphi_lo, f_new, dphi_new);
+        } else {
+            alpha_lo = alpha_current;
+            f_lo = f_new;
+            dphi_lo = dphi_new;
+            if (alpha_hi == INFINITY)
+                alpha_current *= 2;
+            else
+                alpha_current = oracle_safe_cubic(alpha_lo, alpha_hi, f_lo, dphi_lo, f_new, dphi_new);
+        }
+        if (alpha_current < WOLFE_INTERP_MIN) {
+            alpha_current = WOLFE_INTERP_MIN; /* x_temp is updated, x_host is not (:339-346) */
+            break;
+        }
+    }
+    return alpha_current;
+}
+
+/* par/L-BFGS-Interpolation.cu:259-342 */
+static double ls_inl_interpolation(phi_t *p, inl_t *q)
+{
+    const double grad_dot_d = p->gd;
+    double alpha_current = INITIAL_STEP_SIZE;
+    double alpha_prev = 0.0;
+    double f_prev = q->f_initial; /* :265 */
+    const double f_x = q->f_xhost; /* :267 */
+    p->nf++;
+    q->success = 0;
+    for (int iter = 0; iter < 20; ++iter) {
+        const double f_new = inl_f_at(p, q, alpha_current);
+        if (f_new <= f_x + C1 * alpha_current * grad_dot_d) {
+            q->success = 1;
+            break;
+        }
+        if (alpha_current < WOLFE_INTERP_MIN) {
+            alpha_current = WOLFE_INTERP_MIN;
+            break;
+        }
+        if (alpha_prev > 0) {
+            const double delta_alpha = alpha_current - alpha_prev;
+            if (fabs(delta_alpha) < 1e-10) {
+                alpha_current *= 0.5;
+            } else {
+                const double grad_alpha = (f_new - f_x - grad_dot_d * alpha_current) / (alpha_current * alpha_current);
+                double next_alpha = oracle_cubic(alpha_prev, alpha_current, f_prev, grad_dot_d, f_new, grad_alpha);
+                if (next_alpha < 0.1 * alpha_prev || next_alpha > 0.9 * alpha_prev)
+                    next_alpha = alpha_prev * 0.5;
+                alpha_current = next_alpha;
+            }
+        } else {
+            double next_alpha = oracle_quadratic(alpha_current, 0.0, f_new, grad_dot_d, f_x);
+            if (next_alpha < 0.1 * INITIAL_STEP_SIZE || next_alpha > 0.9 * INITIAL_STEP_SIZE)
+                next_alpha = INITIAL_STEP_SIZE * 0.5;
+            alpha_current = next_alpha;
+        }
+        alpha_prev = alpha_current;
+        f_prev = f_new;
+    }
+    if (alpha_current < 1e-4) /* :338-341, after the loop: applies to every exit */
+        alpha_current = 0.5;
+    return alpha_current;
+}
+
+/* par/L-BFGS-Backtracking.cu:292-341 (local constants :153-156; f_current re-read from d_x :308-312) */
+static double ls_inl_backtracking(phi_t *p, inl_t *q)
+{
+    const double lTOL = 1e-10;
+    double step_size = INITIAL_STEP_SIZE;
+    const double f_current = p->f0(p);
+    q->success = 0;
+    for (;;) {
+        const double f_trial = inl_f_at(p, q, step_size);
+        if (f_trial <= f_current + C1 * step_size * p->gd) {
+            q->success = 1;
+            break;
+        }
+        step_size *= BACKTRACKING_ALPHA;
+        if (step_size < lTOL) {
+            step_size = 0.5;
+            break;
+        }
+    }
+    return step_size;
+}
+
+/* par/L-BFGS-Backtracking_Wolfe.cu:262-397 (the unordered_map caches only memoise) */
+static double ls_inl_btwolfe(phi_t *p, inl_t *q)
+{
+    const double lC1 = 1e-4, lC2 = 0.9, lTOL = 1e-10;
+    const double f_x = q->f_xhost; /* :266 */
+    const double grad_dot_d = p->gd;
+    double alpha_current = 1.0, alpha_lo = 0.0, alpha_hi = DBL_MAX;
+    p->nf++;
+    q->success = 0;
+    for (int iter = 0; iter < 20; ++iter) {
+        const double f_new = inl_f_at(p, q, alpha_current);
+        if (f_new <= f_x + lC1 * alpha_current * grad_dot_d) {
+            const double gnd = p->df_at(p, alpha_current);
+            if (gnd >= lC2 * grad_dot_d) {
+                q->success = 1;
+                break;
+            }
+            alpha_lo = alpha_current;
+        } else {
+            alpha_hi = alpha_current;
+        }
+        if (alpha_hi < DBL_MAX)
+            alpha_current = (alpha_lo + alpha_hi) / 2.0;
+        else
+            alpha_current = 2.0 * alpha_lo;
+        if (alpha_current < lTOL) {
+            alpha_current = lTOL;
+            (void)inl_f_at(p, q, alpha_current); /* :371-396: evaluated at TOL, x_host follows */
+            break;
+        }
+    }
+    return alpha_current;
+}
+
+static double run_ls_inlined(int ls, phi_t *p, inl_t *q)
+{
+    switch (ls) {
+    case ORACLE_LS_BACKTRACKING: return ls_inl_backtracking(p, q);
+    case ORACLE_LS_INTERPOLATION: return ls_inl_interpolation(p, q);
+    case ORACLE_LS_WOLFE: return ls_inl_wolfe(p, q);
+    default: return ls_inl_btwolfe(p, q);
+    }
+}
+
 /* ---- 1-D polynomial phi, for the host state-machine tests ---- */
 static double poly_f(phi_t *p, double a)
 {
@@ -429,6 +607,25 @@ static double vec_f0(phi_t *p)
     vec_ctx_t *c = (vec_ctx_t *)p->ctx;
     p->nf++;
     return oracle_f(c->objective, c->x, c->n);
+}
+
+/* inlined searches over the polynomial: f_xhost is what the solver loop would hand over as
+ * "f(x_k)", f_initial as f(x0).  *f_xhost_out = f at the last point the search evaluated. */
+double oracle_ls_poly_inlined(int line_search, const double coef[5], double f_xhost, double f_initial,
+                              int *nf, int *ng, int *success, double *f_xhost_out)
+{
+    phi_t p;
+    memset(&p, 0, sizeof p);
+    p.f_at = poly_f; p.df_at = poly_df; p.f0 = poly_f0;
+    p.gd = coef[1];
+    p.ctx = (void *)coef;
+    inl_t q = { f_xhost, f_initial, 0 };
+    const double a = run_ls_inlined(line_search, &p, &q);
+    if (nf) *nf = (int)p.ntrial;
+    if (ng) *ng = (int)p.ng;
+    if (success) *success = q.success;
+    if (f_xhost_out) *f_xhost_out = q.f_xhost;
+    return a;
 }
 
 /* ------------------------------------------------------------------ */
@@ -599,7 +796,7 @@ int oracle_lbfgs(const oracle_params_t *p, size_t n, const double *x0, double *x
 }
 
 /* ------------------------------------------------------------------ */
-/* CUDA-tree outer loop: par/L-BFGS.cu:195-357 (see the header: unpinned) */
+/* CUDA-tree outer loop: par/L-BFGS.cu:195-357 (see the header for the pin)  */
 /* ------------------------------------------------------------------ */
 int oracle_lbfgs_cuda_profile(const oracle_params_t *p, size_t n, const double *x0, double *x_out,
                               double *trace, size_t trace_rows, oracle_result_t *res)
@@ -614,8 +811,11 @@ int oracle_lbfgs_cuda_profile(const oracle_params_t *p, size_t n, const double *
     double *S = (double *)calloc((size_t)m * n, sizeof(double)), *Y = (double *)calloc((size_t)m * n, sizeof(double));
     double *alpha = (double *)calloc(m, sizeof(double)), *rho = (double *)calloc(m, sizeof(double));
     int *skip = (int *)calloc(m, sizeof(int));
+    inl_t inl = { 0.0, 0.0, 0 };
     memcpy(x, x0, n * sizeof(double));
-    double f_cur = oracle_f(p->objective, x, n); nf++;
+    double f_cur = oracle_f(p->objective, x, n);
+    /* par/L-BFGS.cu and par/L-BFGS-Backtracking.cu never evaluate f(x0) outside a search */
+    if (p->flavor == ORACLE_FLAVOR_PAR_INLINED && p->line_search != ORACLE_LS_BACKTRACKING) nf++;
     oracle_grad(p->objective, x, g, n); ng++; /* :199 */
     int k;
     for (k = 0; k < p->max_iterations; ++k) {
@@ -652,11 +852,29 @@ int oracle_lbfgs_cuda_profile(const oracle_params_t *p, size_t n, const double *
         memset(&phi, 0, sizeof phi);
         phi.f_at = vec_f; phi.df_at = vec_df; phi.f0 = vec_f0;
         phi.gd = oracle_dot(g, d, n); phi.ctx = &c;
-        const double a = run_ls(p->line_search, p->flavor, &phi); /* :293 (with the CURRENT gradient) */
-        nf += phi.nf; ng += phi.ng;
-        if (a < 1e-10) { status = ORACLE_STATUS_LS_FAILED; break; } /* :295-305 */
+        double a;
+        if (p->flavor == ORACLE_FLAVOR_PAR_INLINED) {
+            if (k == 0) { inl.f_xhost = f_cur; inl.f_initial = f_cur; } /* par/L-BFGS-Wolfe.cu:165-172 */
+            a = run_ls_inlined(p->line_search, &phi, &inl);
+            nf += phi.nf; ng += phi.ng;
+            /* par/L-BFGS-Wolfe.cu:353, par/L-BFGS-Interpolation.cu:345, par/L-BFGS-Backtracking_Wolfe.cu:401;
+             * the inlined backtracking has no failure exit */
+            if (p->line_search != ORACLE_LS_BACKTRACKING && !inl.success && a < 1e-10) {
+                status = ORACLE_STATUS_LS_FAILED;
+                break;
+            }
+        } else {
+            a = run_ls(p->line_search, p->flavor, &phi); /* :293 (with the CURRENT gradient) */
+            nf += phi.nf; ng += phi.ng;
+            if (a < 1e-10) { status = ORACLE_STATUS_LS_FAILED; break; } /* :295-305 */
+        }
         for (size_t j = 0; j < n; ++j) xn[j] = x[j] + a * d[j]; /* :309 (no FMA restated) */
-        oracle_grad(p->objective, xn, gn, n); ng++;              /* :323 */
+        oracle_grad(p->objective, xn, gn, n);                    /* :323 */
+        /* the inlined Wolfe searches keep the gradient of the accepted trial instead of evaluating it again
+         * (par/L-BFGS-Wolfe.cu:385-395, par/L-BFGS-Backtracking_Wolfe.cu:432): same values, one call less */
+        if (!(p->flavor == ORACLE_FLAVOR_PAR_INLINED && inl.success &&
+              (p->line_search == ORACLE_LS_WOLFE || p->line_search == ORACLE_LS_BACKTRACKING_WOLFE)))
+            ng++;
         double *s = S + (size_t)(k % m) * n, *y = Y + (size_t)(k % m) * n; /* :332-333 */
         for (size_t j = 0; j < n; ++j) { s[j] = xn[j] - x[j]; y[j] = gn[j] - g[j]; }
         memcpy(x, xn, n * sizeof(double));

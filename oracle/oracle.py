@@ -7,6 +7,9 @@ legs may import this module.  Two things live behind it:
 * ``Ref``     -- oracle/_ref/libref_{seq,hybrid}.so, the UNMODIFIED reference sources
                  compiled by oracle/Makefile (present only after ``make ref`` ran in the
                  build container; the .so files travel to the GPU box).
+* ``CudaRef`` -- oracle/_ref/libref_cuda_*.so, the reference's UNMODIFIED CUDA solvers
+                 (parallel-implementation/*.cu) cross-compiled for sm_100 by ``make cudaref``;
+                 they need a GPU, so only ``-m gpu`` tests and oracle/make_golden_cuda.py run them.
 """
 import ctypes as C
 import os
@@ -19,7 +22,7 @@ REFERENCE_ROOT = "/root/reference"
 
 OBJ = {"quadratic": 0, "rosenbrock": 1, "tridiag": 2}
 LS = {"backtracking": 0, "interpolation": 1, "wolfe": 2, "backtracking_wolfe": 3}
-FLAVOR = {"seq": 0, "par": 1}
+FLAVOR = {"seq": 0, "par": 1, "par_inlined": 2}
 TRACE_COLS = 8
 TR_K, TR_F, TR_GNORM, TR_ALPHA, TR_TRIALS, TR_HIST, TR_X0, TR_XMID = range(8)
 
@@ -34,7 +37,7 @@ def build(ref=True):
     """Compile the restatement and, where /root/reference exists, the reference itself."""
     subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
     if ref and os.path.isdir(REFERENCE_ROOT):
-        subprocess.check_call(["make", "-s", "-C", HERE, "ref", "refmain"])
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref", "refmain", "cudaref"])
 
 
 class _Params(C.Structure):
@@ -122,6 +125,17 @@ class Oracle:
         a = self.L.oracle_ls_poly(LS[line_search], FLAVOR[flavor], _p(c), C.byref(nf), C.byref(ng))
         return a, nf.value, ng.value
 
+    def ls_poly_inlined(self, line_search, coef, f_xhost, f_initial):
+        """-> (alpha, trials, grad_evals, success, f at the last evaluated point)"""
+        coef = np.ascontiguousarray(coef, dtype=np.float64)
+        nf, ng, ok, fl = C.c_int(), C.c_int(), C.c_int(), C.c_double()
+        self.L.oracle_ls_poly_inlined.restype = C.c_double
+        self.L.oracle_ls_poly_inlined.argtypes = [C.c_int, _dp, C.c_double, C.c_double, C.POINTER(C.c_int),
+                                                  C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        a = self.L.oracle_ls_poly_inlined(LS[line_search], _p(coef), f_xhost, f_initial, C.byref(nf), C.byref(ng),
+                                          C.byref(ok), C.byref(fl))
+        return a, nf.value, ng.value, ok.value, fl.value
+
     def lbfgs(self, objective, x0, line_search="backtracking", flavor="seq", m=10,
               max_iterations=1000, tolerance=1e-5, trace_rows=0, profile="seq"):
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
@@ -201,3 +215,47 @@ class Ref:
         st = self.L.ref_lbfgs(OBJ[objective], LS[line_search], x0.size, _p(x0), max_iterations, m,
                               tolerance, _p(x), C.byref(nf), C.byref(ng), C.byref(sec))
         return x, dict(status=st, f_evals=nf.value, g_evals=ng.value, seconds=sec.value)
+
+
+class CudaRef:
+    """The reference's own CUDA solver (one of parallel-implementation/*.cu), run as-is on the GPU."""
+
+    VARIANTS = {"host": "par/L-BFGS.cu", "wolfe": "par/L-BFGS-Wolfe.cu", "backtracking": "par/L-BFGS-Backtracking.cu",
+                "interpolation": "par/L-BFGS-Interpolation.cu", "btwolfe": "par/L-BFGS-Backtracking_Wolfe.cu"}
+
+    def __init__(self, variant):
+        assert variant in self.VARIANTS, variant
+        path = os.path.join(HERE, "_ref", "libref_cuda_%s.so" % variant)
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " (run `make -C oracle cudaref` in the build container)")
+        self.variant = variant
+        L = self.L = C.CDLL(path)
+        L.ref_cuda_lbfgs.restype = C.c_int
+        L.ref_cuda_lbfgs.argtypes = [C.c_int, C.c_char_p, C.c_size_t, _dp, C.c_int, C.c_int, C.c_double, _dp,
+                                     C.POINTER(C.c_long), C.POINTER(C.c_long), C.c_char_p, C.c_size_t]
+
+    @staticmethod
+    def available(variant):
+        return os.path.exists(os.path.join(HERE, "_ref", "libref_cuda_%s.so" % variant))
+
+    def lbfgs(self, objective, x0, line_search="wolfe", m=10, max_iterations=1000, tolerance=1e-5):
+        """Returns (x, info); info["log"] is the reference's stdout, info["alphas"] / ["gnorms"] are parsed
+        from its "alpha: ..." / "Iteration k: norm_g = ..." lines (6 significant digits, as printed)."""
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        x = np.empty_like(x0)
+        nf, ng = C.c_long(), C.c_long()
+        cap = 1 << 22
+        log = C.create_string_buffer(cap)
+        rc = self.L.ref_cuda_lbfgs(OBJ[objective], line_search.encode(), x0.size, _p(x0), max_iterations, m, tolerance,
+                                   _p(x), C.byref(nf), C.byref(ng), log, cap)
+        if rc != 0:
+            raise RuntimeError("the CUDA reference threw")
+        text = log.value.decode(errors="replace")
+        alphas, gnorms = [], []
+        for line in text.splitlines():
+            if line.startswith("alpha: "):
+                alphas.append(float(line.split()[1]))
+            elif line.startswith("Iteration ") and "norm_g" in line:
+                gnorms.append(float(line.rsplit("=", 1)[1]))
+        status = 2 if "Line search failed" in text else (0 if "Convergence achieved" in text else 1)
+        return x, dict(status=status, f_evals=nf.value, g_evals=ng.value, log=text, alphas=alphas, gnorms=gnorms)

@@ -53,6 +53,13 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def cuda_golden():
+    """Outputs of the reference's own CUDA solvers run on a B200 (oracle/make_golden_cuda.py)."""
+    with open(os.path.join(ROOT, "tests", "golden", "cuda_reference_traces.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.fixture(scope="session")
 def gpu(pkg):
     """The library on a machine with a device; GPU tests fail (not skip) if the extension is
     missing or no device is visible."""

@@ -16,15 +16,42 @@ extern "C" double harness_ls_poly(int kind, int flavor, const double *coef, int 
     p.flavor = flavor;
     p.max_trials = 20;
     p.c1 = 1e-4;
-    p.c2 = flavor == FLAVOR_PAR ? 0.7 : 0.9;
+    p.c2 = flavor != FLAVOR_SEQ ? 0.7 : 0.9;
     p.step0 = 1.0;
     p.shrink = 0.5;
     p.bt_tol = 1e-8;
     p.wolfe_min = 1e-10;
-    LsState s;
+    LsState s = {};
     int go = ls_begin(p, s, coef[0], coef[1]);
     while (go) go = ls_step(p, s, poly(coef, s.alpha), dpoly(coef, s.alpha));
     if (trials) *trials = s.trials;
+    return s.alpha;
+}
+
+// FLAVOR_PAR_INLINED: the previous search left x_host at a point with f = f_xhost (stale), f(x0) = f_initial.
+// *f_xhost_out = what the NEXT search would take as f(x_k): f_last if this search returned a step it did not
+// evaluate, f at the returned step otherwise.
+extern "C" double harness_ls_poly_inlined(int kind, const double *coef, double f_xhost, double f_initial, int *trials,
+                                          int *success, double *f_xhost_out)
+{
+    LsParams p;
+    p.kind = kind;
+    p.flavor = FLAVOR_PAR_INLINED;
+    p.max_trials = 20;
+    p.c1 = 1e-4;
+    p.c2 = 0.7;
+    p.step0 = 1.0;
+    p.shrink = 0.5;
+    p.bt_tol = 1e-10; // par/L-BFGS-Backtracking.cu:155
+    p.wolfe_min = 1e-10;
+    LsState s = {};
+    s.stale = 1;
+    s.f_last = f_xhost;
+    int go = ls_begin(p, s, coef[0], coef[1], f_initial);
+    while (go) go = ls_step(p, s, poly(coef, s.alpha), dpoly(coef, s.alpha));
+    if (trials) *trials = s.trials;
+    if (success) *success = s.success;
+    if (f_xhost_out) *f_xhost_out = s.stale ? s.f_last : poly(coef, s.alpha);
     return s.alpha;
 }
 

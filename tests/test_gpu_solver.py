@@ -387,9 +387,9 @@ def test_curvature_gate_skip_path(gpu, oracle, direction):
 def test_cuda_profile_matches_its_restatement(gpu, oracle, direction):
     """profile=CUDA (par/L-BFGS.cu outer loop: slot always overwritten, pairs with s.y<=1e-10 skipped,
     gamma fallback, <= test after the step, no descent safeguard) against oracle_lbfgs_cuda_profile.
-    That restatement is unpinned (the CUDA reference cannot run in the build container) and omits the
-    reference's stale-state bugs, exactly like the product; this checks the two agree with each other,
-    including on starts where pairs with negative curvature are stored and skipped."""
+    That restatement is pinned against the reference's CUDA solvers run on a B200 (tests/test_oracle.py,
+    tests/test_gpu_cuda_reference.py) and omits two stale-state bugs of par/L-BFGS.cu, exactly like the product;
+    this adds starts where pairs with negative curvature are stored and skipped."""
     cases = [("rosenbrock", 10000, (-2, 2), "wolfe", 10, 20, None), ("tridiag", 10000, (-2, 2), "interpolation", 5, 30, None),
              ("rosenbrock", 6, (-4, 4), "backtracking", 30, 25, 35), ("rosenbrock", 50, (-4, 4), "interpolation", 3, 25, 33),
              ("quadratic", 5000, (-1000, 1000), "backtracking", 10, 10, None)]

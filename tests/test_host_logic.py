@@ -56,6 +56,36 @@ def test_line_search_state_machines_match_oracle(harness, oracle):
     assert n_checked == 4000 * 8
 
 
+def test_inlined_cuda_line_searches_match_oracle(harness, oracle):
+    """FLAVOR_PAR_INLINED (the searches inlined in par/L-BFGS-{Wolfe,Interpolation,Backtracking,Backtracking_Wolfe}.cu):
+    step, trial count, success flag and the f(x_host) handed to the next search, decision by decision."""
+    harness.harness_ls_poly_inlined.restype = C.c_double
+    harness.harness_ls_poly_inlined.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_double, C.c_double,
+                                                C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    rng = np.random.default_rng(23)
+    seen_fail = seen_multi = 0
+    for trial in range(4000):
+        scale = 10.0 ** rng.integers(-3, 4)
+        coef = np.array([rng.uniform(-5, 5), -abs(rng.normal()) * scale, rng.normal() * scale,
+                         rng.normal() * scale * (trial % 3 == 0), abs(rng.normal()) * scale * (trial % 2 == 0)])
+        # the stale f(x_host) is near f(x_k), f(x0) is well above it -- as in a real run
+        f_xhost = coef[0] + (rng.normal() * 1e-3 * scale if trial % 4 == 0 else 0.0)
+        f_initial = coef[0] + abs(rng.normal()) * 100.0 * scale
+        p = coef.ctypes.data_as(C.POINTER(C.c_double))
+        for kind, name in enumerate(("backtracking", "interpolation", "wolfe", "backtracking_wolfe")):
+            tr, ok, fl = C.c_int(), C.c_int(), C.c_double()
+            a = harness.harness_ls_poly_inlined(kind, p, f_xhost, f_initial, C.byref(tr), C.byref(ok), C.byref(fl))
+            want, nf, ng, wok, wfl = oracle.ls_poly_inlined(name, coef, f_xhost, f_initial)
+            assert _same(a, want), (name, coef, a, want)
+            assert ok.value == wok, (name, coef)
+            # the oracle counts the extra evaluation at TOL of the bisection search as a trial
+            assert tr.value == nf or (name == "backtracking_wolfe" and tr.value + 1 == nf), (name, coef, tr.value, nf)
+            assert _same(fl.value, wfl), (name, coef, fl.value, wfl)
+            seen_fail += not wok
+            seen_multi += nf > 1
+    assert seen_fail > 50 and seen_multi > 1000
+
+
 def test_line_search_trial_counts(harness, oracle):
     # phi(a) = 1 - a + 50 a^2 : steep valley, forces several shrink steps
     coef = np.array([1.0, -1.0, 50.0, 0.0, 0.0])
