@@ -18,6 +18,9 @@ Prints ONE JSON line (rank 0).  Keys beyond the base contract:
                   Wolfe search = the hybrid oracle) on one host core, on a bounded sample
   e2e          -- same metric through the host-buffer API: create + H2D x0 + W+K iterations +
                   D2H x, wall clock
+  reference_cuda_on_this_gpu -- the reference's own CUDA solver for this configuration
+                  (parallel-implementation/L-BFGS-Wolfe.cu, unmodified, cross-compiled for sm_100 under
+                  oracle/_ref) timed on the same GPU on the same bounded sample as cpu_baseline
 
 --impl reference times only the reference's CPU implementation (rank 0; other ranks exit 0).
 """
@@ -127,6 +130,36 @@ def cpu_reference_rate(steps, warmup, n_sample=CPU_SAMPLE_N):
                       "%.3f s/iteration, scaled linearly in n to n=%d" % (n_sample, N_GLOBAL // n_sample, steps, warm,
                                                                         per_iter, N_GLOBAL),
             "host_cores_available": os.cpu_count(), "seconds_per_iteration_at_sample": per_iter}
+
+
+def cuda_reference_rate(steps, warmup, n_sample=CPU_SAMPLE_N):
+    """The reference's own CUDA solver for this configuration (parallel-implementation/L-BFGS-Wolfe.cu, unmodified,
+    cross-compiled for sm_100: oracle/_ref/libref_cuda_wolfe.so) on the SAME B200: steady-state seconds per
+    iteration on n_sample elements, scaled linearly to N_GLOBAL.  Its iteration ships x and the gradient across
+    PCIe and evaluates f / grad on one host core, so linear scaling in n is exact to first order.
+    None when the library was not built (it needs /root/reference at build time)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as om
+    if OBJECTIVE != "rosenbrock" or LINE_SEARCH != "wolfe" or not om.CudaRef.available("wolfe"):
+        return None
+    ref = om.CudaRef("wolfe")
+    x0 = om.Oracle().x0(n_sample, -2, 2)
+
+    def run(iters):
+        t = time.perf_counter()
+        ref.lbfgs(OBJECTIVE, x0, "wolfe", M, iters, 0.0)
+        return time.perf_counter() - t
+    warm = max(warmup, 1)
+    run(1)  # CUDA context / cuBLAS initialisation of that library
+    t_warm = run(warm)
+    t_all = run(warm + steps)
+    per_iter = max(t_all - t_warm, 1e-9) / steps
+    return {"value": (1.0 / per_iter) * n_sample / N_GLOBAL, "unit": "iterations/s", "kind": "reference (CUDA tree)",
+            "source": "parallel-implementation/L-BFGS-Wolfe.cu, unmodified, nvcc defaults, sm_100, cuBLAS; 1 GPU + 1 host core",
+            "sample": "n=%d (1/%d of the workload) x %d steady-state iterations after %d warm-up, measured %.4f "
+                      "s/iteration, scaled linearly in n to n=%d" % (n_sample, N_GLOBAL // n_sample, steps, warm, per_iter,
+                                                                     N_GLOBAL),
+            "seconds_per_iteration_at_sample": per_iter}
 
 
 def run_reference_arm(args):
@@ -315,8 +348,13 @@ def main():
                    "byte counts are the one-off 8n-byte copies amortised over the iterations of the call" % (FILL + W + K)}
 
     cpu_baseline = None
+    cuda_reference = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = cpu_reference_rate(min(K, 20), 12)
+        try:
+            cuda_reference = cuda_reference_rate(min(K, 20), 12)
+        except Exception as e:  # the comparison is informative, never fatal to the bench line
+            cuda_reference = {"unavailable": repr(e)}
 
     if rank == 0:
         line = {"metric": "L-BFGS iterations/sec (FP64) at n=%.0e, m=%d" % (n_global, M) if (n_global != N_GLOBAL or M != 10) else "L-BFGS iterations/sec (FP64) at n=1e8, m=10", "value": main_run["value"], "unit": "iterations/s",
@@ -331,7 +369,7 @@ def main():
                            "trials_per_step": main_run["trials_per_step"],
                            "history_fill_iterations_before_warmup": FILL},
                 "wall_ms_per_step": main_run["wall_ms_per_step"], "gpu_launches": main_run["gpu_launches"],
-                "clocks": main_run["clocks"], "roofline": main_run["roofline"], "e2e": e2e, "cpu_baseline": cpu_baseline,
+                "clocks": main_run["clocks"], "roofline": main_run["roofline"], "e2e": e2e, "cpu_baseline": cpu_baseline, "reference_cuda_on_this_gpu": cuda_reference,
                 "final": main_run["final"]}
         if other_run is not None:
             line["variants"] = {other: {k: other_run[k] for k in ("value", "ms_per_step", "gpu_launches", "trials_per_step", "final")}}
