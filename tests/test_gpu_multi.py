@@ -32,3 +32,18 @@ def test_sharded_equals_single_gpu(gpu, args):
         pytest.skip("needs >= 2 GPUs")
     out = _run(min(ndev, 2), *args)
     assert out["ok"], out
+
+
+@pytest.mark.parametrize("args", [
+    ("--obj", "rosenbrock", "--ls", "wolfe", "--flavor", "par", "--size", "1000003", "--dir", "compact", "--graph", "1"),
+    ("--obj", "rosenbrock", "--ls", "interpolation", "--flavor", "par", "--size", "400009", "--hist", "20", "--dir", "compact"),
+    ("--obj", "tridiag", "--ls", "wolfe", "--flavor", "par", "--size", "250001", "--iters", "9"),
+])
+def test_sharded_equals_single_gpu_on_every_device_of_the_node(gpu, args):
+    """The same comparison with one rank per visible device (4 or 8): the mailbox exchange with more than one
+    peer, the 3(2m+1)-row Gram exchange, odd shard sizes."""
+    ndev = gpu.lib().lbfgsb200_device_count()
+    if ndev < 4:
+        pytest.skip("needs >= 4 GPUs")
+    out = _run(min(ndev, 8), *args)
+    assert out["ok"], out
