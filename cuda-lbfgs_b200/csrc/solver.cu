@@ -711,15 +711,24 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     // release threshold raised, so that destroying a solver and creating the next one of similar size
     // re-uses the mapping instead of paying cudaMalloc/cudaFree of tens of GB (5-130 ms each way) again.
     // lbfgsb200_trim_memory() hands the cached memory back to the driver.
+    cudaMemPool_t pool;
     {
         int dev = 0;
-        cudaMemPool_t pool;
         CREATE_TRY(cudaGetDevice(&dev));
         CREATE_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
         uint64_t keep = UINT64_MAX;
         CREATE_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
     cudaError_t e = cudaMallocAsync(&s->arena, arena_bytes, s->stream);
+    if (e == cudaErrorMemoryAllocation) {
+        // an arena cached from a destroyed solver of another size may be what is in the way: give the
+        // cache back to the driver and try once more
+        cudaGetLastError();
+        s->arena = nullptr;
+        cudaStreamSynchronize(s->stream);
+        cudaMemPoolTrimTo(pool, 0);
+        e = cudaMallocAsync(&s->arena, arena_bytes, s->stream);
+    }
     if (e != cudaSuccess) {
         set_error("allocation of %.2f GB for %zu vectors failed: %s", arena_bytes / 1e9, nvecs, cudaGetErrorString(e));
         cudaGetLastError();
