@@ -18,9 +18,13 @@
 //
 // Objectives: host std::function callbacks cannot run inside the device-resident iteration loop.
 // The shim identifies which built-in device objective a callback pair IS by evaluating it on two
-// fixed 6-element probe vectors and comparing f and grad bit-for-bit with the built-ins
+// fixed probe vectors OF THE PROBLEM'S DIMENSION (the reference's tridiagonal generator assert()s on
+// the dimension it was built for, sequential-implementation/benchmark.cpp:18, :38 -- a shorter probe
+// would abort the process) and comparing f and grad with the built-ins
 // (parallel-implementation/functions.cpp:6-49, sequential-implementation/benchmark.cpp:16-56).
-// Anything else throws std::invalid_argument -- there is deliberately no CPU fallback.
+// That costs two f and two grad calls of the caller's functions; compat_options().objective names the
+// objective directly and skips it.  Anything else throws std::invalid_argument -- there is
+// deliberately no CPU fallback.
 #ifndef LBFGSB200_COMPAT_HPP
 #define LBFGSB200_COMPAT_HPP
 
@@ -34,15 +38,16 @@ namespace lbfgsb200 {
 struct CompatOptions {
     int flavor = -1;          // -1: LBFGS -> SEQ tree, LBFGS_CUDA(method) -> PAR tree, LBFGS_CUDA() -> inlined searches
     int profile = -1;         // -1: LBFGS -> SEQ outer loop, LBFGS_CUDA -> CUDA outer loop
+    int objective = -1;       // -1: recognise the callbacks by probing; else LBFGSB200_OBJ_* (no probing)
     int direction = LBFGSB200_DIR_TWO_LOOP;
     int use_graph = 0;
     const char *cuda_default_line_search = "wolfe"; // for the LBFGS_CUDA overload without a method
     lbfgsb200_result_t last_result;                 // filled by every call (the reference only prints)
 };
 CompatOptions &compat_options();
-// returns LBFGSB200_OBJ_* or -1
+// returns LBFGSB200_OBJ_* or -1; n = the dimension the callbacks are called with
 int identify_objective(const std::function<double(std::vector<double>)> &f,
-                       const std::function<std::vector<double>(std::vector<double>)> &grad);
+                       const std::function<std::vector<double>(std::vector<double>)> &grad, size_t n = 6);
 } // namespace lbfgsb200
 
 #ifdef LBFGSB200_COMPAT_IMPLEMENTATION
@@ -107,30 +112,36 @@ inline bool close(double a, double b)
 } // namespace detail
 
 int identify_objective(const std::function<double(std::vector<double>)> &f,
-                       const std::function<std::vector<double>(std::vector<double>)> &grad)
+                       const std::function<std::vector<double>(std::vector<double>)> &grad, size_t n)
 {
-    const std::vector<double> probes[2] = {{0.3, -1.2, 0.7, 1.9, -0.4, 1.1},
-                                           {1.5, 0.25, -0.8, 0.05, 2.2, -1.7}};
-    for (int obj = LBFGSB200_OBJ_QUADRATIC; obj <= LBFGSB200_OBJ_TRIDIAG; ++obj) {
-        bool ok = true;
-        for (const auto &p : probes) {
-            double fv;
-            std::vector<double> gv;
-            try {
-                fv = f(p);
-                gv = grad(p);
-            } catch (...) { // e.g. the tridiagonal generator asserts on the dimension
-                ok = false;
-                break;
-            }
-            if (!detail::close(fv, detail::builtin_f(obj, p)) || gv.size() != p.size()) { ok = false; break; }
-            const std::vector<double> want = detail::builtin_g(obj, p);
-            for (size_t i = 0; i < p.size(); ++i)
-                if (!detail::close(gv[i], want[i])) ok = false;
-            if (!ok) break;
+    // two probes of length n: a period-6 and a period-7 pattern, so neighbouring pairs differ along the vector
+    static const double base[2][7] = {{0.3, -1.2, 0.7, 1.9, -0.4, 1.1, 0.0}, {1.5, 0.25, -0.8, 0.05, 2.2, -1.7, 0.6}};
+    if (n == 0) return -1;
+    bool candidate[3] = {true, true, true};
+    for (int k = 0; k < 2; ++k) {
+        std::vector<double> p(n);
+        for (size_t i = 0; i < n; ++i) p[i] = base[k][i % (size_t)(6 + k)];
+        double fv;
+        std::vector<double> gv;
+        try { // the caller's functions are evaluated once per probe, whatever the number of candidates
+            fv = f(p);
+            gv = grad(p);
+        } catch (...) {
+            return -1;
         }
-        if (ok) return obj;
+        if (gv.size() != n) return -1;
+        for (int obj = LBFGSB200_OBJ_QUADRATIC; obj <= LBFGSB200_OBJ_TRIDIAG; ++obj) {
+            if (!candidate[obj]) continue;
+            bool ok = detail::close(fv, detail::builtin_f(obj, p));
+            if (ok) {
+                const std::vector<double> want = detail::builtin_g(obj, p);
+                for (size_t i = 0; i < n && ok; ++i) ok = detail::close(gv[i], want[i]);
+            }
+            candidate[obj] = ok;
+        }
     }
+    for (int obj = LBFGSB200_OBJ_QUADRATIC; obj <= LBFGSB200_OBJ_TRIDIAG; ++obj)
+        if (candidate[obj]) return obj;
     return -1;
 }
 
@@ -147,7 +158,7 @@ inline std::vector<double> run(const std::function<double(std::vector<double>)> 
     else if (method == "wolfe") ls = LBFGSB200_LS_WOLFE;
     else if (method == "backtracking_wolfe") ls = LBFGSB200_LS_BACKTRACKING_WOLFE;
     else throw std::invalid_argument("Unknown line search method: " + method); // seq/lbfgs.cpp:69
-    const int obj = identify_objective(f, grad);
+    const int obj = o.objective >= 0 ? o.objective : identify_objective(f, grad, x0.size());
     if (obj < 0)
         throw std::invalid_argument(
             "lbfgsb200: the objective is not one of the built-in device objectives (quadratic, rosenbrock, "

@@ -188,3 +188,27 @@ def test_header_is_plain_c(tmp_path):
                    % os.path.join(ROOT, "include", "lbfgsb200.h"))
     cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
     subprocess.check_call([cc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", str(src)])
+
+
+def test_compat_shim_host_behaviour(pkg, tmp_path):
+    """include/lbfgsb200_compat.hpp without a GPU: objective recognition and the reference's exceptions
+    (seq/lbfgs.cpp:69 for an unknown method; a foreign objective is refused instead of run on the CPU)."""
+    pkg.lib()
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    exe = str(tmp_path / "compat_host_check")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++14", "-O1", "-Wall", os.path.join(ROOT, "tests", "compat_host_check.cpp"),
+                           "-L" + libdir, "-llbfgsb200", "-Wl,-rpath," + libdir, "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = dict(line.split(": ", 1) for line in r.stdout.strip().splitlines())
+    assert got["quadratic"] == "0" and got["rosenbrock"] == "1" and got["tridiag6"] == "2"
+    # the reference's tridiagonal generator assert()s on its dimension (seq/benchmark.cpp:18): probes have that size
+    assert "ABORT" not in r.stdout
+    assert got["tridiag10000"] == "2" and got["rosenbrock4097"] == "1" and got["quadratic1"] == "0"
+    assert got["bound_objective"].startswith("solved 64") or "no usable CUDA device" in got["bound_objective"] \
+        or "no CPU fallback" in got["bound_objective"], got["bound_objective"]
+    assert got["named_objective"] == "invalid_argument Unknown line search method: newton"
+    assert got["quartic"] == "-1" and got["mismatched_gradient"] == "-1"
+    assert got["unknown_method"] == "invalid_argument Unknown line search method: newton"
+    assert got["foreign_objective"].startswith("invalid_argument lbfgsb200: the objective is not one of the built-in")
