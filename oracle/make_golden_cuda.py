@@ -36,6 +36,18 @@ CASES = [
     ("host_interpolation_quad_1e4", "host", "interpolation", "quadratic", 10000, (-1000, 1000), 10, 0.0, [1, 2, 3]),
 ]
 
+# run-to-convergence cases from starts near the minimiser, where the iteration count is stable under rounding
+# (SURVEY.md App. D); the reference mains' own tolerance (1e-1) and a tighter one.
+# (name, variant, line_search argument, objective, n, (lo, hi), m, tol, max_iterations)
+FINAL_CASES = [
+    ("wolfe_rosen_1e4_near_final", "wolfe", None, "rosenbrock", 10000, (0.5, 1.5), 10, 1e-1, 1000),
+    ("wolfe_rosen_1e4_near_tight_final", "wolfe", None, "rosenbrock", 10000, (0.5, 1.5), 10, 1e-5, 1000),
+    ("interpolation_rosen_1e4_near_final", "interpolation", None, "rosenbrock", 10000, (0.5, 1.5), 10, 1e-1, 1000),
+    ("backtracking_rosen_1e4_near_final", "backtracking", None, "rosenbrock", 10000, (0.5, 1.5), 10, 1e-1, 1000),
+    ("btwolfe_rosen_1e4_near_final", "btwolfe", None, "rosenbrock", 10000, (0.5, 1.5), 10, 1e-1, 1000),
+    ("wolfe_quad_1e4_final", "wolfe", None, "quadratic", 10000, (-1000, 1000), 10, 1e-8, 100),
+]
+
 
 def hx(v):
     return float(v).hex()
@@ -69,6 +81,17 @@ def main():
                                    lo=lo, hi=hi, m=m, tolerance=tol, x0_first=hx(x0[0]), x0_last=hx(x0[-1]), steps=steps,
                                    stdout_of_longest_run=log[:6000])
         print(name, "ok", "alphas", steps[str(max(Ks))]["alphas_printed"][:8], flush=True)
+    out["finals"] = {}
+    for name, variant, ls, obj, n, (lo, hi), m, tol, max_it in FINAL_CASES:
+        ref = CudaRef(variant)
+        x0 = host.x0(n, lo, hi)
+        x, info = ref.lbfgs(obj, x0, ls or "wolfe", m, max_it, tol)
+        g = host.grad(obj, x)
+        out["finals"][name] = dict(variant=variant, source_file=CudaRef.VARIANTS[variant], line_search=ls, objective=obj, n=n,
+                                   lo=lo, hi=hi, m=m, tolerance=tol, max_iterations=max_it, status=info["status"],
+                                   iterations=len(info["gnorms"]), f=hx(host.f(obj, x)), gnorm=hx(host.norm(g)),
+                                   f_evals=info["f_evals"], g_evals=info["g_evals"], x_first=hx(x[0]), x_mid=hx(x[n // 2]))
+        print(name, "status", info["status"], "iterations", len(info["gnorms"]), flush=True)
     with open(out_path, "w") as fh:
         json.dump(out, fh, indent=1, sort_keys=True)
     print("wrote", os.path.normpath(out_path))
