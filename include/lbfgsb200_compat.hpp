@@ -29,6 +29,7 @@
 #define LBFGSB200_COMPAT_HPP
 
 #include <functional>
+#include <ostream>
 #include <string>
 #include <vector>
 
@@ -45,6 +46,11 @@ struct CompatOptions {
     lbfgsb200_result_t last_result;                 // filled by every call (the reference only prints)
 };
 CompatOptions &compat_options();
+// What the CUDA tree's solvers print while they run (unconditionally: parallel-implementation/L-BFGS-Wolfe.cu:114
+// "Starting", :351 "alpha: ...", :415-416 "Iteration k: norm_g = ..." / "Optimum value: ...", :420 "Convergence
+// achieved at iteration k"; L-BFGS.cu:297 "Warning: Line search failed at iteration k"), rebuilt from the
+// device trace (LBFGSB200_TRACE_COLS doubles per completed iteration).  LBFGS_CUDA() prints it after the solve.
+void print_cuda_log(std::ostream &os, const double *trace, size_t rows, long long iterations, int status);
 // returns LBFGSB200_OBJ_* or -1; n = the dimension the callbacks are called with
 int identify_objective(const std::function<double(std::vector<double>)> &f,
                        const std::function<std::vector<double>(std::vector<double>)> &grad, size_t n = 6);
@@ -145,6 +151,21 @@ int identify_objective(const std::function<double(std::vector<double>)> &f,
     return -1;
 }
 
+void print_cuda_log(std::ostream &os, const double *trace, size_t rows, long long iterations, int status)
+{
+    os << "Starting" << std::endl;
+    for (long long k = 0; k < iterations && (size_t)k < rows; ++k) {
+        const double *row = trace + (size_t)k * LBFGSB200_TRACE_COLS; // k, f, |g|, alpha, trials, h, x[0], x[n/2]
+        os << "alpha: " << row[3] << std::endl;
+        os << "Iteration " << k << ": norm_g = " << row[2] << std::endl;
+        os << "Optimum value: " << row[1] << std::endl;
+    }
+    if (status == LBFGSB200_CONVERGED && iterations > 0)
+        os << "Convergence achieved at iteration " << iterations - 1 << std::endl;
+    else if (status == LBFGSB200_LS_FAILED)
+        os << "Warning: Line search failed at iteration " << iterations << std::endl;
+}
+
 namespace detail {
 inline std::vector<double> run(const std::function<double(std::vector<double>)> &f,
                                const std::function<std::vector<double>(std::vector<double>)> &grad,
@@ -177,7 +198,7 @@ inline std::vector<double> run(const std::function<double(std::vector<double>)> 
     std::vector<double> x(x0.size());
     std::vector<double> trace;
     size_t rows = 0;
-    if (verbose) {
+    if (verbose || cuda_entry) {
         rows = (size_t)(max_iterations < 100000 ? max_iterations : 100000);
         trace.resize(rows * LBFGSB200_TRACE_COLS + 1);
     }
@@ -186,6 +207,10 @@ inline std::vector<double> run(const std::function<double(std::vector<double>)> 
     if (rc < 0) { // the reference prints the CUDA error and exit(EXIT_FAILURE)s (par/L-BFGS.cu:76-83)
         std::cerr << "lbfgsb200: " << lbfgsb200_strerror(rc) << " (" << lbfgsb200_last_error() << ")" << std::endl;
         throw std::runtime_error(lbfgsb200_last_error());
+    }
+    if (cuda_entry) { // the CUDA tree's own progress lines, then its silence about "maximum iterations"
+        print_cuda_log(std::cout, trace.data(), rows, (long long)o.last_result.iterations, rc);
+        return x;
     }
     if (verbose) {
         // seq/lbfgs.cpp:76-78: one line at the top of every iteration k with the current f and |grad|

@@ -8,7 +8,10 @@
 
 #include <cmath>
 #include <cstdio>
+#include <iostream>
 #include <stdexcept>
+
+#include "../oracle/lbfgs_oracle.h" // test infrastructure: supplies a trace for print_cuda_log
 
 using std::function;
 using std::string;
@@ -105,6 +108,22 @@ int main()
         std::printf("bound_objective: invalid_argument %s\n", e.what());
     } catch (const std::runtime_error &e) {
         std::printf("bound_objective: runtime_error %s\n", e.what());
+    }
+    // the CUDA tree's progress lines, rebuilt from a trace: the restatement of par/L-BFGS-Wolfe.cu on the golden
+    // case wolfe_rosen_1e4 (the test compares this text with the stdout the reference printed on a B200)
+    {
+        const size_t n = 10000;
+        const int K = 20;
+        vector<double> xs(n), xo(n), tr((size_t)K * ORACLE_TRACE_COLS);
+        oracle_x0(42, -2, 2, n, xs.data());
+        oracle_params_t op = {ORACLE_OBJ_ROSENBROCK, ORACLE_LS_WOLFE, ORACLE_FLAVOR_PAR_INLINED, 10, K, 0.0};
+        oracle_result_t res;
+        const int status = oracle_lbfgs_cuda_profile(&op, n, xs.data(), xo.data(), tr.data(), K, &res);
+        std::printf("cuda_log_begin: %d\n", status);
+        std::fflush(stdout);
+        lbfgsb200::print_cuda_log(std::cout, tr.data(), K, res.iterations, status);
+        std::cout.flush();
+        std::printf("cuda_log_end: %ld\n", res.iterations);
     }
     // naming the objective skips the probing altogether
     lbfgsb200::compat_options().objective = LBFGSB200_OBJ_ROSENBROCK;

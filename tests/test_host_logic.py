@@ -197,11 +197,17 @@ def test_compat_shim_host_behaviour(pkg, tmp_path):
     libdir = os.path.dirname(pkg.LIB_PATH)
     exe = str(tmp_path / "compat_host_check")
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    odir = os.path.join(ROOT, "oracle")
+    subprocess.check_call(["make", "-s", "-C", odir, "oracle"])
     subprocess.check_call([cxx, "-std=c++14", "-O1", "-Wall", os.path.join(ROOT, "tests", "compat_host_check.cpp"),
-                           "-L" + libdir, "-llbfgsb200", "-Wl,-rpath," + libdir, "-o", exe])
+                           "-L" + libdir, "-llbfgsb200", "-L" + odir, "-llbfgs_oracle", "-Wl,-rpath," + libdir,
+                           "-Wl,-rpath," + odir, "-o", exe])
     r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0, r.stdout + r.stderr
-    got = dict(line.split(": ", 1) for line in r.stdout.strip().splitlines())
+    lines = r.stdout.strip().splitlines()
+    b, e = [i for i, l in enumerate(lines) if l.startswith("cuda_log_begin")][0], [i for i, l in enumerate(lines) if l.startswith("cuda_log_end")][0]
+    cuda_log, lines = lines[b + 1:e], lines[:b] + lines[e + 1:]
+    got = dict(line.split(": ", 1) for line in lines)
     assert got["quadratic"] == "0" and got["rosenbrock"] == "1" and got["tridiag6"] == "2"
     # the reference's tridiagonal generator assert()s on its dimension (seq/benchmark.cpp:18): probes have that size
     assert "ABORT" not in r.stdout
@@ -209,6 +215,18 @@ def test_compat_shim_host_behaviour(pkg, tmp_path):
     assert got["bound_objective"].startswith("solved 64") or "no usable CUDA device" in got["bound_objective"] \
         or "no CPU fallback" in got["bound_objective"], got["bound_objective"]
     assert got["named_objective"] == "invalid_argument Unknown line search method: newton"
+    # LBFGS_CUDA's progress output: same lines as the reference's CUDA solver printed on a B200 for this case
+    # (tests/golden/cuda_reference_traces.json), numbers to the 6 significant digits of operator<<
+    import json
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "cuda_reference_traces.json")))["traces"]["wolfe_rosen_1e4"]
+    want = want["stdout_of_longest_run"].strip().splitlines()
+    assert len(cuda_log) == len(want) == 1 + 3 * 20, (len(cuda_log), len(want))
+    for g, w in zip(cuda_log, want):
+        gl, gv = g.rsplit(" ", 1) if " " in g else (g, None)
+        wl, wv = w.rsplit(" ", 1) if " " in w else (w, None)
+        assert gl == wl, (g, w)
+        if wv is not None:
+            assert abs(float(gv) - float(wv)) <= 2e-5 * abs(float(wv)), (g, w)
     assert got["quartic"] == "-1" and got["mismatched_gradient"] == "-1"
     assert got["unknown_method"] == "invalid_argument Unknown line search method: newton"
     assert got["foreign_objective"].startswith("invalid_argument lbfgsb200: the objective is not one of the built-in")
