@@ -817,6 +817,8 @@ int oracle_lbfgs_cuda_profile(const oracle_params_t *p, size_t n, const double *
     /* par/L-BFGS.cu and par/L-BFGS-Backtracking.cu never evaluate f(x0) outside a search */
     if (p->flavor == ORACLE_FLAVOR_PAR_INLINED && p->line_search != ORACLE_LS_BACKTRACKING) nf++;
     oracle_grad(p->objective, x, g, n); ng++; /* :199 */
+    double *g0 = (double *)malloc(n * sizeof(double));
+    memcpy(g0, g, n * sizeof(double));
     int k;
     for (k = 0; k < p->max_iterations; ++k) {
         if (k == 0) {
@@ -851,7 +853,8 @@ int oracle_lbfgs_cuda_profile(const oracle_params_t *p, size_t n, const double *
         phi_t phi;
         memset(&phi, 0, sizeof phi);
         phi.f_at = vec_f; phi.df_at = vec_df; phi.f0 = vec_f0;
-        phi.gd = oracle_dot(g, d, n); phi.ctx = &c;
+        /* par/L-BFGS.cu:293 passes `gradient`, assigned once at k == 0 (:199) */
+        phi.gd = oracle_dot(p->flavor == ORACLE_FLAVOR_PAR_STALE_GRADIENT ? g0 : g, d, n); phi.ctx = &c;
         double a;
         if (p->flavor == ORACLE_FLAVOR_PAR_INLINED) {
             if (k == 0) { inl.f_xhost = f_cur; inl.f_initial = f_cur; } /* par/L-BFGS-Wolfe.cu:165-172 */
@@ -864,7 +867,7 @@ int oracle_lbfgs_cuda_profile(const oracle_params_t *p, size_t n, const double *
                 break;
             }
         } else {
-            a = run_ls(p->line_search, p->flavor, &phi); /* :293 (with the CURRENT gradient) */
+            a = run_ls(p->line_search, ORACLE_FLAVOR_PAR, &phi); /* :293 (with the CURRENT gradient unless ..._STALE_GRADIENT) */
             nf += phi.nf; ng += phi.ng;
             if (a < 1e-10) { status = ORACLE_STATUS_LS_FAILED; break; } /* :295-305 */
         }
@@ -898,7 +901,7 @@ int oracle_lbfgs_cuda_profile(const oracle_params_t *p, size_t n, const double *
         res->gnorm = oracle_norm(gn, n);
     }
     free(x); free(g); free(d); free(q); free(xn); free(gn); free(xt); free(gt);
-    free(S); free(Y); free(alpha); free(rho); free(skip);
+    free(S); free(Y); free(alpha); free(rho); free(skip); free(g0);
     (void)f_cur;
     return status;
 }

@@ -22,7 +22,7 @@ REFERENCE_ROOT = "/root/reference"
 
 OBJ = {"quadratic": 0, "rosenbrock": 1, "tridiag": 2}
 LS = {"backtracking": 0, "interpolation": 1, "wolfe": 2, "backtracking_wolfe": 3}
-FLAVOR = {"seq": 0, "par": 1, "par_inlined": 2}
+FLAVOR = {"seq": 0, "par": 1, "par_inlined": 2, "par_stale_gradient": 3}
 TRACE_COLS = 8
 TR_K, TR_F, TR_GNORM, TR_ALPHA, TR_TRIALS, TR_HIST, TR_X0, TR_XMID = range(8)
 
