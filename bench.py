@@ -259,10 +259,13 @@ def main():
     V = 8.0 * n_local
     h = M
     # algorithmic bytes per launch of each streaming-kernel class
-    class_bytes = {"two_loop_pass": (8 * h - 1) * V / (2 * h), "gram_rows": (2 * h + 1) * V, "combine": (2 * h + 2) * V,
-                   "trial": 2 * V, "accept": 7 * V}
-    class_kernel = {"two_loop_pass": "k_two_loop_pass", "gram_rows": "k_gram_tma2d" if M > 6 else "k_gram_tma", "combine": "k_combine",
-                    "trial": "k_trial", "accept": "k_accept"}
+    fused = os.environ.get("LBFGSB200_FUSED", "1") != "0"
+    # fused compact flow (default): k_accept_gram reads the 2(h-1) kept history rows + x, d, g and writes x, g, s, y;
+    # k_combine_trial reads the 2h+1 basis vectors + x and writes d (the first line-search trial rides on it)
+    class_bytes = {"two_loop_pass": (8 * h - 1) * V / (2 * h), "gram_rows": ((2 * (h - 1) + 7) if fused else (2 * h + 1)) * V,
+                   "combine": ((2 * h + 3) if fused else (2 * h + 2)) * V, "trial": 2 * V, "accept": 7 * V}
+    class_kernel = {"two_loop_pass": "k_two_loop_pass", "gram_rows": "k_accept_gram" if fused else "k_gram_tma2d",
+                    "combine": "k_combine_trial" if fused else "k_combine", "trial": "k_trial", "accept": "k_accept"}
     traffic_db = {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):

@@ -31,7 +31,7 @@ OBJ = {"quadratic": 0, "rosenbrock": 1, "tridiag": 2}
 LS = {"backtracking": 0, "interpolation": 1, "wolfe": 2, "backtracking_wolfe": 3}
 FLAVOR = {"seq": 0, "par": 1, "par_inlined": 2}
 PROFILE = {"seq": 0, "cuda": 1}
-DIRECTION = {"two_loop": 0, "compact": 1}
+DIRECTION = {"two_loop": 0, "compact": 1, "auto": 2}
 STATUS = {0: "converged", 1: "max_iter", 2: "ls_failed", 3: "running"}
 TRACE_COLS = 8
 UNIQUE_ID_BYTES = 128
@@ -45,7 +45,7 @@ class Params(C.Structure):
                 ("direction", C.c_int), ("c1", C.c_double), ("c2", C.c_double),
                 ("step0", C.c_double), ("shrink", C.c_double), ("backtracking_tol", C.c_double),
                 ("wolfe_min", C.c_double), ("ls_max_trials", C.c_int), ("use_graph", C.c_int),
-                ("verbose", C.c_int), ("grid_ctas", C.c_int)]
+                ("verbose", C.c_int), ("grid_ctas", C.c_int), ("num_gpus", C.c_int)]
 
 
 class Result(C.Structure):
@@ -75,6 +75,7 @@ EXPORTS = [
     "lbfgsb200_two_loop", "lbfgsb200_accept", "lbfgsb200_x0_uniform", "lbfgsb200_host_alloc",
     "lbfgsb200_host_free", "lbfgsb200_device_alloc", "lbfgsb200_device_free", "lbfgsb200_memcpy",
     "lbfgsb200_set_device", "lbfgsb200_device_sync", "lbfgsb200_trim_memory", "lbfgsb200_mem_info", "lbfgsb200_debug_timeline",
+    "lbfgsb200_resolve_num_gpus", "lbfgsb200_comm_create_local",
 ]
 
 
@@ -140,6 +141,8 @@ def lib():
     L.lbfgsb200_device_free.argtypes = [C.c_void_p]
     L.lbfgsb200_memcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.lbfgsb200_set_device.argtypes = [C.c_int]
+    L.lbfgsb200_resolve_num_gpus.argtypes = [C.c_int, C.c_size_t]
+    L.lbfgsb200_resolve_num_gpus.restype = C.c_int
     _lib = L
     return L
 
@@ -346,6 +349,7 @@ def solve(objective, x0, line_search="backtracking", flavor="seq", trace_rows=0,
     """One-shot lbfgsb200_solve() on host buffers: the call a user of the reference's
     ``LBFGS(f, grad, x0, method, max_iterations, m, tolerance)`` makes."""
     x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    overrides.setdefault("num_gpus", 1)  # explicit: the automatic choice depends on the box
     p = default_params(flavor, line_search=line_search, **overrides)
     x = np.empty_like(x0)
     r = Result()

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "liblbfgsb200.so")
 SOURCES = ["solver.cu", "comm.cpp", "x0gen.cpp"]
-HEADERS = ["state.h", "ls_logic.h", "kernels.cuh", "scalar_ops.cuh", "comm.h", "compact.cuh", "comm.cpp", "x0gen.cpp",
+HEADERS = ["state.h", "ls_logic.h", "kernels.cuh", "scalar_ops.cuh", "comm.h", "compact.cuh", "accept_gram.cuh", "comm.cpp", "x0gen.cpp",
            os.path.join("..", "..", "include", "lbfgsb200.h")]
 
 
@@ -37,10 +37,10 @@ def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []  # dynamic libstdc++
     cmd = [nvcc_path()] + ccbin + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared",
+           "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-O2,-pthread", "-shared",
            "-Xptxas", "-v" if verbose else "-O3"]
     cmd += [os.path.join(CSRC, f) for f in SOURCES]
-    cmd += ["-ldl", "-o", LIB]  # NCCL is dlopen()ed at run time (csrc/comm.cpp)
+    cmd += ["-ldl", "-lpthread", "-o", LIB]  # NCCL is dlopen()ed at run time (csrc/comm.cpp)
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -70,15 +70,17 @@ int comm_allgather(lbfgsb200_comm *c, const double *send, double *recv, int coun
 } // namespace lb
 
 namespace lb {
-// Allocate this rank's mailbox, exchange the CUDA IPC handles through NCCL, map every peer's
-// mailbox.  All ranks must agree on the outcome, so the local verdict is all-gathered too.
+// Allocate this rank's mailbox, exchange the CUDA IPC handles through NCCL, map every peer's mailbox.  Every
+// fallible LOCAL step (allocations, mappings, the upload of the pointer table) happens before the last agreement
+// round, and its outcome is part of what that round gathers: all ranks reach the same verdict, so none is left
+// spinning on a mailbox while its peers sit in NCCL.  On a negative verdict everything is released again.
 int setup_mailboxes(lbfgsb200_comm *c)
 {
     const int P = c->nranks;
-    // data + flags + one more row of 64-bit words whose first entry is the exchange counter
-    const size_t mail_doubles = (size_t)2 * LBFGSB200_MAIL_RANKS * LBFGSB200_MAIL_WIDTH + (size_t)3 * LBFGSB200_MAIL_RANKS;
+    const size_t mail_bytes = LBFGSB200_MAIL_DOUBLES * sizeof(double);
     int dev = 0;
     cudaGetDevice(&dev);
+    c->device = dev;
     struct Blob {
         cudaIpcMemHandle_t handle;
         int device;
@@ -88,12 +90,18 @@ int setup_mailboxes(lbfgsb200_comm *c)
     memset(&mine, 0, sizeof mine);
     mine.device = dev;
     mine.ok = 1;
-    if (cudaMalloc(&c->mail, mail_doubles * sizeof(double)) != cudaSuccess) mine.ok = 0;
-    if (mine.ok && cudaMemset(c->mail, 0, mail_doubles * sizeof(double)) != cudaSuccess) mine.ok = 0;
-    if (mine.ok && cudaIpcGetMemHandle(&mine.handle, c->mail) != cudaSuccess) mine.ok = 0;
-    cudaGetLastError();
     char *d_buf = nullptr;
-    if (cudaMalloc(&d_buf, sizeof(Blob) * (size_t)(P + 1)) != cudaSuccess) return -1;
+    if (cudaMalloc(&c->mail, mail_bytes) != cudaSuccess) mine.ok = 0;
+    if (mine.ok && cudaMemset(c->mail, 0, mail_bytes) != cudaSuccess) mine.ok = 0;
+    if (mine.ok && cudaIpcGetMemHandle(&mine.handle, c->mail) != cudaSuccess) mine.ok = 0;
+    if (cudaMalloc(&c->peers_dev, sizeof(double *) * (size_t)P) != cudaSuccess) mine.ok = 0;
+    // the gather buffer itself: without it this rank cannot even take part in the agreement, so it is the one
+    // failure that has to be reported as "no NCCL exchange possible either"
+    if (cudaMalloc(&d_buf, sizeof(Blob) * (size_t)(P + 1)) != cudaSuccess) {
+        cudaGetLastError();
+        return -2;
+    }
+    cudaGetLastError();
     std::vector<Blob> all((size_t)P);
     auto gather = [&]() -> int {
         if (cudaMemcpy(d_buf, &mine, sizeof mine, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
@@ -102,31 +110,99 @@ int setup_mailboxes(lbfgsb200_comm *c)
         if (cudaMemcpy(all.data(), d_buf + sizeof(Blob), sizeof(Blob) * (size_t)P, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
         return 0;
     };
-    if (gather() != 0) { cudaFree(d_buf); return -1; }
+    int rc = gather(); // round 1: handles
     std::vector<double *> peers((size_t)P, nullptr);
-    for (int r = 0; r < P && mine.ok; ++r) {
-        if (!all[r].ok) { mine.ok = 0; break; }
-        if (r == c->rank) { peers[r] = c->mail; continue; }
-        int can = 0;
-        if (cudaDeviceCanAccessPeer(&can, dev, all[r].device) != cudaSuccess || !can) { mine.ok = 0; break; }
-        void *p = nullptr;
-        if (cudaIpcOpenMemHandle(&p, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { mine.ok = 0; break; }
-        c->opened[r] = p;
-        peers[r] = (double *)p;
+    if (rc == 0) {
+        for (int r = 0; r < P && mine.ok; ++r) {
+            if (!all[r].ok) { mine.ok = 0; break; }
+            if (r == c->rank) { peers[r] = c->mail; continue; }
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, dev, all[r].device) != cudaSuccess || !can) { mine.ok = 0; break; }
+            void *p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { mine.ok = 0; break; }
+            c->opened[r] = p;
+            peers[r] = (double *)p;
+        }
+        if (mine.ok && cudaMemcpy(c->peers_dev, peers.data(), sizeof(double *) * (size_t)P, cudaMemcpyHostToDevice) != cudaSuccess) mine.ok = 0;
+        cudaGetLastError();
+        rc = gather(); // round 2: every rank learns whether EVERY rank mapped everything
     }
-    cudaGetLastError();
-    // second round: every rank learns whether EVERY rank mapped everything
-    if (gather() != 0) { cudaFree(d_buf); return -1; }
     cudaFree(d_buf);
-    int all_ok = 1;
-    for (int r = 0; r < P; ++r) all_ok &= all[r].ok;
-    if (!all_ok) return -1;
-    if (cudaMalloc(&c->peers_dev, sizeof(double *) * (size_t)P) != cudaSuccess) return -1;
-    if (cudaMemcpy(c->peers_dev, peers.data(), sizeof(double *) * (size_t)P, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+    int all_ok = (rc == 0);
+    for (int r = 0; r < P && all_ok; ++r) all_ok &= all[r].ok;
+    if (!all_ok) { // identical on every rank (a failed gather fails on all of them): fall back together
+        for (int r = 0; r < LBFGSB200_MAIL_RANKS; ++r)
+            if (c->opened[r]) { cudaIpcCloseMemHandle(c->opened[r]); c->opened[r] = nullptr; }
+        if (c->peers_dev) { cudaFree(c->peers_dev); c->peers_dev = nullptr; }
+        if (c->mail) { cudaFree(c->mail); c->mail = nullptr; }
+        cudaGetLastError();
+        return -1;
+    }
     c->p2p = 1;
     return 0;
 }
 } // namespace lb
+
+// In-process communicator: P devices driven by threads of ONE process (lbfgsb200_solve with num_gpus > 1).
+// Mailboxes are plain device allocations made reachable with cudaDeviceEnablePeerAccess; no NCCL, no IPC.
+extern "C" int lbfgsb200_comm_create_local(lbfgsb200_comm_t **out, const int *devices, int nranks)
+{
+    if (!out || !devices || nranks < 1 || nranks > LBFGSB200_MAIL_RANKS) {
+        lb::set_error("comm_create_local: bad arguments (%d ranks, at most %d)", nranks, LBFGSB200_MAIL_RANKS);
+        return LBFGSB200_ERR_INVALID;
+    }
+    int saved = 0;
+    cudaGetDevice(&saved);
+    for (int r = 0; r < nranks; ++r) out[r] = nullptr;
+    const size_t mail_bytes = LBFGSB200_MAIL_DOUBLES * sizeof(double);
+    int rc = 0;
+    std::vector<double *> mails((size_t)nranks, nullptr);
+    for (int r = 0; r < nranks && !rc; ++r) {
+        lbfgsb200_comm *c = new lbfgsb200_comm;
+        memset(c, 0, sizeof *c);
+        c->rank = r;
+        c->nranks = nranks;
+        c->local = 1;
+        c->device = devices[r];
+        out[r] = c;
+        if (cudaSetDevice(devices[r]) != cudaSuccess) { lb::set_error("comm_create_local: cannot select device %d", devices[r]); rc = LBFGSB200_ERR_CUDA; break; }
+        for (int q = 0; q < nranks && !rc; ++q) {
+            if (q == r || devices[q] == devices[r]) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[r], devices[q]) != cudaSuccess || !can) {
+                lb::set_error("comm_create_local: device %d cannot access device %d (no NVLink / peer access)", devices[r], devices[q]);
+                rc = LBFGSB200_ERR_CUDA;
+                break;
+            }
+            cudaError_t e = cudaDeviceEnablePeerAccess(devices[q], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                lb::set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", devices[r], devices[q], cudaGetErrorString(e));
+                rc = LBFGSB200_ERR_CUDA;
+            }
+            cudaGetLastError();
+        }
+        if (!rc && (cudaMalloc(&c->mail, mail_bytes) != cudaSuccess || cudaMemset(c->mail, 0, mail_bytes) != cudaSuccess ||
+                    cudaMalloc(&c->peers_dev, sizeof(double *) * (size_t)nranks) != cudaSuccess)) {
+            lb::set_error("comm_create_local: mailbox allocation failed on device %d", devices[r]);
+            rc = LBFGSB200_ERR_NOMEM;
+        }
+        mails[r] = c->mail;
+    }
+    for (int r = 0; r < nranks && !rc; ++r) {
+        cudaSetDevice(devices[r]);
+        if (cudaMemcpy(out[r]->peers_dev, mails.data(), sizeof(double *) * (size_t)nranks, cudaMemcpyHostToDevice) != cudaSuccess) {
+            lb::set_error("comm_create_local: upload of the mailbox table failed on device %d", devices[r]);
+            rc = LBFGSB200_ERR_CUDA;
+        }
+        out[r]->p2p = nranks > 1 ? 1 : 0;
+    }
+    if (rc) {
+        for (int r = 0; r < nranks; ++r)
+            if (out[r]) { lbfgsb200_comm_destroy(out[r]); out[r] = nullptr; }
+    }
+    cudaSetDevice(saved);
+    return rc;
+}
 
 static_assert(sizeof(ncclUniqueId) <= LBFGSB200_UNIQUE_ID_BYTES, "unique id does not fit");
 
@@ -165,10 +241,11 @@ extern "C" int lbfgsb200_comm_create(lbfgsb200_comm_t **out, const char id[LBFGS
     c->nccl = comm;
     c->rank = rank;
     c->nranks = nranks;
+    cudaGetDevice(&c->device);
     *out = c;
     const char *env = getenv("LBFGSB200_P2P");
     if (nranks > 1 && nranks <= LBFGSB200_MAIL_RANKS && !(env && atoi(env) == 0)) {
-        if (lb::setup_mailboxes(c) != 0) { // not fatal: keep the NCCL exchange
+        if (lb::setup_mailboxes(c) != 0) { // not fatal, and the same verdict on every rank: keep the NCCL exchange
             c->p2p = 0;
         }
     }
@@ -178,11 +255,12 @@ extern "C" int lbfgsb200_comm_create(lbfgsb200_comm_t **out, const char id[LBFGS
 extern "C" void lbfgsb200_comm_destroy(lbfgsb200_comm_t *c)
 {
     if (!c) return;
+    if (c->local) cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (int r = 0; r < LBFGSB200_MAIL_RANKS; ++r)
         if (c->opened[r]) cudaIpcCloseMemHandle(c->opened[r]);
     if (c->peers_dev) cudaFree(c->peers_dev);
     if (c->mail) cudaFree(c->mail);
-    if (lb::g_nccl.handle) lb::g_nccl.CommDestroy((ncclComm_t)c->nccl);
+    if (c->nccl && lb::g_nccl.handle) lb::g_nccl.CommDestroy((ncclComm_t)c->nccl);
     delete c;
 }

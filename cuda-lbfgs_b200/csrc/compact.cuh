@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kThreads, kGramCtasPerSm)
 k_gram(const DevState *__restrict__ st, int T, int NS, int G)
 {
     const int h = st->h;
-    if (st->ctrl.done || st->steepest || h == 0) return;
+    if (st->ctrl.done || h == 0 || (st->steepest && !st->sg_valid)) return; // rows of a fresh pair are needed even if d = -g
     extern __shared__ __align__(128) double tile[]; // [NS][Jt][T]
     __shared__ const double *cols[kMaxCols];
     const int J = 2 * h + 1;
@@ -159,11 +159,10 @@ k_gram(const DevState *__restrict__ st, int T, int NS, int G)
     }
 }
 
-// ---- pass A, TMA variant -------------------------------------------------------------------
-// Same arithmetic, but the tiles are moved by the copy engine: a producer warp issues ONE
-// cp.async.bulk (1-D TMA, SASS UBLKCP) per basis vector and tile, completion is counted in bytes
-// on an mbarrier per stage, and kGramStages stages are kept in flight.  No per-thread copy
-// instructions (the LDGSTS version spends ~40% of its MIO slots issuing copies), shared memory is
+// ---- pass A, TMA variants ------------------------------------------------------------------
+// Same arithmetic, but the tiles are moved by the copy engine (tensor-map TMA, below): completion is
+// counted in bytes on an mbarrier per stage, and kGramStages stages are kept in flight.  No per-thread
+// copy instructions (the LDGSTS version spends ~40% of its MIO slots issuing copies), shared memory is
 // read back with 128-bit loads, and the consumer warps are split into NG column groups x 16/NG
 // element groups so that each row value is re-read NG times.
 constexpr int kGramStages = 4;
@@ -190,124 +189,20 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         if (spin > (1 << 24)) __trap(); // a lost copy must fail the launch, never hang the GPU
     }
 }
-__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // Warp-specialised pass A: ONE CTA per SM owning ~200 KB of shared memory.
-//   warp 0            producer: per tile, one cp.async.bulk (1-D TMA) per basis vector into the next
-//                     free stage; completion is counted in bytes on full[stage]
+//   warp 0            producer: per tile, <= 5 tiled TMA loads into the next free stage; completion is
+//                     counted in bytes on full[stage]
 //   warps 1..16       consumers: wait on full[stage], reduce their (column group, element group) share
 //                     of the tile with 128-bit shared-memory loads, then release the stage by arriving
 //                     on empty[stage] -- no CTA-wide barrier inside the loop
 // kGramStages-1 whole tiles (all 2h+1 vectors) per SM are in flight while one is being reduced.
 constexpr int kWsConsumerWarps = 16;
 constexpr int kWsThreads = 32 * (kWsConsumerWarps + 1);
-
-template <int CW>
-__global__ void __launch_bounds__(kWsThreads, 1) k_gram_tma(const DevState *__restrict__ st, int T, int NG)
-{
-    const int h = st->h;
-    if (st->ctrl.done || st->steepest || h == 0) return;
-    extern __shared__ __align__(128) double tile[]; // [kGramStages][J][T]
-    __shared__ const double *cols[kMaxCols];
-    __shared__ __align__(8) unsigned long long full[kGramStages], empty[kGramStages];
-    const int J = 2 * h + 1;
-    const long long npad = st->stride; // rows are zero-padded to a multiple of 32 doubles
-    for (int j = threadIdx.x; j < J; j += kWsThreads) cols[j] = basis_col(st, j, h);
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kGramStages; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kWsConsumerWarps);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long ntiles = (st->n + T - 1) / T;
-    const size_t stage_doubles = (size_t)J * T;
-    const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int NE = kWsConsumerWarps / NG;
-    double acc[CW][3];
-#pragma unroll
-    for (int c = 0; c < CW; ++c) acc[c][0] = acc[c][1] = acc[c][2] = 0.0;
-    const int cw = warp - 1, cg = cw % NG, eg = cw / NG; // consumer coordinates (warp >= 1)
-
-    if (warp == 0) {
-        // ---------------- producer ----------------
-        for (long long k = 0; k < my_tiles; ++k) {
-            const int stage = (int)(k % kGramStages);
-            if (k >= kGramStages) mbar_wait(&empty[stage], (unsigned)(((k / kGramStages) - 1) & 1));
-            const long long base = (blockIdx.x + k * (long long)gridDim.x) * T;
-            long long valid = npad - base;
-            if (valid > T) valid = T;
-            double *dst = tile + stage * stage_doubles;
-            if (lane == 0) mbar_expect_tx(&full[stage], (unsigned)(J * valid * sizeof(double)));
-            __syncwarp();
-            for (int j = lane; j < J; j += 32)
-                tma_load_1d(dst + (size_t)j * T, cols[j] + base, (unsigned)(valid * sizeof(double)), &full[stage]);
-        }
-    } else {
-        // ---------------- consumers ----------------
-        const int r0 = h - 1, r1 = 2 * h - 1, r2 = 2 * h;
-        const int T2 = T >> 1, slice2 = T2 / NE;
-        for (long long k = 0; k < my_tiles; ++k) {
-            const int stage = (int)(k % kGramStages);
-            mbar_wait(&full[stage], (unsigned)((k / kGramStages) & 1));
-            const long long base = (blockIdx.x + k * (long long)gridDim.x) * T;
-            long long valid = npad - base;
-            if (valid > T) valid = T;
-            const double2 *cur = reinterpret_cast<const double2 *>(tile + stage * stage_doubles);
-            const int e_end = min((eg + 1) * slice2, (int)(valid >> 1));
-            for (int e = eg * slice2 + lane; e < e_end; e += 32) {
-                const double2 a0 = cur[r0 * T2 + e], a1 = cur[r1 * T2 + e], a2 = cur[r2 * T2 + e];
-#pragma unroll
-                for (int c = 0; c < CW; ++c) {
-                    const int j = cg + c * NG;
-                    if (j < J) {
-                        const double2 v = cur[j * T2 + e];
-                        acc[c][0] = fma(a0.y, v.y, fma(a0.x, v.x, acc[c][0]));
-                        acc[c][1] = fma(a1.y, v.y, fma(a1.x, v.x, acc[c][1]));
-                        acc[c][2] = fma(a2.y, v.y, fma(a2.x, v.x, acc[c][2]));
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]); // this warp is done reading the stage
-        }
-    }
-    __syncthreads(); // all tiles consumed; the tile storage can be reused for the reduction
-    // cross-warp reduction (fixed order over the NE element groups), one partial per (column,row)
-    double *red = tile; // [NE][J*3]
-    if (warp > 0) {
-#pragma unroll
-        for (int c = 0; c < CW; ++c) {
-            const int j = cg + c * NG;
-            if (j < J) { // warp-uniform
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    const double s = warp_sum(acc[c][r]);
-                    if (lane == 0) red[eg * (J * 3) + j * 3 + r] = s;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    for (int q = threadIdx.x; q < J * 3; q += kWsThreads) {
-        double s = 0.0;
-        for (int g = 0; g < NE; ++g) s += red[g * (J * 3) + q];
-        st->partials[(size_t)q * gridDim.x + blockIdx.x] = s;
-    }
-}
 
 // ---- pass A, tensor-map TMA variant ---------------------------------------------------------
 // The (s, y) ring buffers are 2-D tensors [slot][element] with a fixed row stride, and the window
@@ -318,11 +213,16 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_gram_tma(const DevState *__re
 // (the box shape is part of the map) and live in global memory.  Out-of-range columns of the last
 // tile are zero-filled by the TMA unit, and the transaction count is always the full box.
 // Producer / consumer structure, tile layout and arithmetic are those of k_gram_tma.
-struct GramMaps {          // device array, one entry per run length r = 1..nslots (index r)
-    CUtensorMap s[kMaxSlots + 1];
-    CUtensorMap y[kMaxSlots + 1];
-    CUtensorMap g;         // 1 x T box over the gradient
+// Tensor maps over the WHOLE arena, a row-major [4 + 2 nslots][stride] FP64 tensor (rows: x, x_alt, g, w,
+// S slots, Y slots): run[r] = box of T columns x r rows (r consecutive ring slots, or one of x / d / g with
+// r = 1), halo = box of 2 columns x 1 row (the element just outside a tile, accept_gram.cuh).  Out-of-range
+// columns (negative or >= stride) are zero-filled by the TMA unit and still count for the full box in the
+// transaction bytes.  Built on the host per solver (cuTensorMapEncodeTiled) and kept in global memory.
+struct ArenaMaps {
+    CUtensorMap run[kMaxSlots + 1];
+    CUtensorMap halo;
 };
+constexpr int kArenaRowX = 0, kArenaRowG = 2, kArenaRowW = 3, kArenaRowS = 4;
 
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1,
                                             unsigned long long *bar)
@@ -336,10 +236,10 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
 
 template <int CW>
 __global__ void __launch_bounds__(kWsThreads, 1)
-k_gram_tma2d(const DevState *__restrict__ st, const GramMaps *__restrict__ maps, int T, int NG)
+k_gram_tma2d(const DevState *__restrict__ st, const ArenaMaps *__restrict__ maps, int T, int NG)
 {
     const int h = st->h;
-    if (st->ctrl.done || st->steepest || h == 0) return;
+    if (st->ctrl.done || h == 0 || (st->steepest && !st->sg_valid)) return;
     extern __shared__ __align__(128) double tile[]; // [kGramStages][J][T]
     __shared__ __align__(8) unsigned long long full[kGramStages], empty[kGramStages];
     const int J = 2 * h + 1;
@@ -373,11 +273,11 @@ k_gram_tma2d(const DevState *__restrict__ st, const GramMaps *__restrict__ maps,
                 const int col = (int)((blockIdx.x + k * (long long)gridDim.x) * T);
                 double *dst = tile + stage * stage_doubles;
                 mbar_expect_tx(&full[stage], bytes);
-                tma_load_2d(dst, &maps->s[ra], col, base_slot, &full[stage]);
-                if (rb) tma_load_2d(dst + (size_t)ra * T, &maps->s[rb], col, 0, &full[stage]);
-                tma_load_2d(dst + (size_t)h * T, &maps->y[ra], col, base_slot, &full[stage]);
-                if (rb) tma_load_2d(dst + (size_t)(h + ra) * T, &maps->y[rb], col, 0, &full[stage]);
-                tma_load_2d(dst + (size_t)(2 * h) * T, &maps->g, col, 0, &full[stage]);
+                tma_load_2d(dst, &maps->run[ra], col, kArenaRowS + base_slot, &full[stage]);
+                if (rb) tma_load_2d(dst + (size_t)ra * T, &maps->run[rb], col, kArenaRowS, &full[stage]);
+                tma_load_2d(dst + (size_t)h * T, &maps->run[ra], col, kArenaRowS + ns + base_slot, &full[stage]);
+                if (rb) tma_load_2d(dst + (size_t)(h + ra) * T, &maps->run[rb], col, kArenaRowS + ns, &full[stage]);
+                tma_load_2d(dst + (size_t)(2 * h) * T, &maps->run[1], col, kArenaRowG, &full[stage]);
             }
         }
     } else {
@@ -432,7 +332,7 @@ k_gram_tma2d(const DevState *__restrict__ st, const GramMaps *__restrict__ maps,
 __global__ void __launch_bounds__(kScalarThreads) k_gram_finalize(DevState *st, int nparts)
 {
     const int h = st->h;
-    if (st->ctrl.done || st->steepest || h == 0) return;
+    if (st->ctrl.done || h == 0 || (st->steepest && !st->sg_valid)) return;
     const int q = blockIdx.x;
     if (q >= 3 * (2 * h + 1)) return;
     __shared__ double sm[kScalarThreads / 32];
@@ -457,7 +357,9 @@ __global__ void __launch_bounds__(kScalarThreads) k_gram_finalize(DevState *st, 
 // rows: the finalised 3 x J inner products of pass A (already summed over ranks on multi-GPU).
 // Gs: J*J doubles of shared memory; the window Gram matrix is staged there so that the 2h dependent
 // steps of the recursion run at shared-memory latency (in HBM they cost ~1.4 us each: 29 us at m = 10).
-__device__ void compact_recursion(DevState *st, const double *rows, double *Gs)
+// fresh: the newest pair was committed by the last accept, so its rows are new.  run == false: only the Gram
+// bookkeeping (the direction is d = -g anyway, but later iterations need the rows of this pair).
+__device__ void compact_recursion(DevState *st, const double *rows, double *Gs, int fresh, bool run)
 {
     const int h = st->h, J = 2 * h + 1, ns = st->nslots, NB = 2 * ns + 1;
     const bool seq = st->profile == LBFGSB200_PROFILE_SEQ;
@@ -470,7 +372,6 @@ __device__ void compact_recursion(DevState *st, const double *rows, double *Gs)
     }
     __syncthreads();
     const int is_new = bi[h - 1], iy_new = bi[2 * h - 1], ig = 2 * ns;
-    const int fresh = st->sg_valid; // the newest pair was committed by the last accept: its rows are new
     for (int j = threadIdx.x; j < J; j += kScalarThreads) {
         const int b = bi[j];
         if (fresh) {
@@ -496,7 +397,7 @@ __device__ void compact_recursion(DevState *st, const double *rows, double *Gs)
         Gs[idx] = G[bi[a] * NB + bi[b]];
     }
     __syncthreads();
-    if (threadIdx.x >= 32) return;
+    if (!run || threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
     int bad = 0;
     // first loop, newest -> oldest (seq/lbfgs.cpp:100-114)
@@ -540,9 +441,20 @@ __device__ void compact_recursion(DevState *st, const double *rows, double *Gs)
     for (int j = lane; j < J; j += 32) st->delta[j] = delta[j];
     if (lane == 0) {
         st->gamma = gamma;
+        if (st->fused && st->nranks > 1) {
+            // the neighbours' boundary d, with the fma chain of k_combine_trial on THEIR boundary elements
+            // (DevState::bL / bR): bit-identical to what they compute, and known before the combine pass runs
+            double sl = 0.0, sr = 0.0;
+            for (int j = 0; j < J; ++j) {
+                sl = fma(delta[j], st->bL[bi[j]], sl);
+                sr = fma(delta[j], st->bR[bi[j]], sr);
+            }
+            st->dL = -sl;
+            st->dR = -sr;
+        }
         if (bad) { // non-finite rho / bad gamma => d = -g (:103-108, :119-124)
             st->steepest = 1;
-            st->vec_streams += 2.0;
+            if (!st->fused) st->vec_streams += 2.0; // the fused flow accounts for its direction pass in OP_F_DIR
         }
     }
 }

@@ -407,7 +407,29 @@ struct EvalCtx {
     double alpha;
     long long n, goff, nglob;
     double xtL, xtR; // trial values of the neighbour shards' boundary elements (halo)
+    double *d_store; // PEND trials only: where d = -g is written
 };
+
+// PEND (fused compact flow, rare): the descent safeguard (seq/lbfgs.cpp:147-153) fired after the combine pass, so
+// the direction in memory is stale.  The trial then reads g instead, uses d = -g and stores it for the later
+// trials and the accept step -- no separate d = -g pass, no extra launch in the common case.
+template <bool PEND>
+__device__ __forceinline__ double2 load_d2(const EvalCtx &c, long long j)
+{
+    double2 v = ld2(c.d, j);
+    if (PEND) {
+        v.x = -v.x;
+        v.y = -v.y;
+        st2(c.d_store, j, v);
+    }
+    return v;
+}
+template <bool PEND>
+__device__ __forceinline__ double load_d1(const EvalCtx &c, long long e)
+{
+    const double v = c.d[e];
+    return PEND ? -v : v;
+}
 
 // trial value of local element e, which may be one outside the shard (halo)
 __device__ __forceinline__ double fetch_xt(const EvalCtx &c, long long e)
@@ -415,6 +437,13 @@ __device__ __forceinline__ double fetch_xt(const EvalCtx &c, long long e)
     if (e < 0) return c.xtL;
     if (e >= c.n) return c.xtR;
     return c.x[e] + c.alpha * c.d[e];
+}
+template <bool PEND>
+__device__ __forceinline__ double fetch_xt_p(const EvalCtx &c, long long e)
+{
+    if (e < 0) return c.xtL;
+    if (e >= c.n) return c.xtR;
+    return c.x[e] + c.alpha * load_d1<PEND>(c, e);
 }
 
 // MODE_TRIAL: sums f, g.d, g.g, optional g store.  (replaces updateSolution + host f/grad +
@@ -438,7 +467,7 @@ struct EvalOut {
 // ex/ed: (unguarded path) the x and d of the one element outside the warp's 64-element span that
 // lane 0 (element 2j-1) or lane 31 (element 2j+2) needs, prefetched by the caller in the same
 // batch as the main loads so the stencil never waits for a second, dependent memory round trip.
-template <class OBJ, int MODE, bool GUARD>
+template <class OBJ, int MODE, bool GUARD, bool PEND = false>
 __device__ __forceinline__ void eval_item(const EvalCtx &c, long long j, long long nvec, bool active,
                                           double2 x2, double2 d2, double2 go, double ex, double ed,
                                           const EvalOut &o, double (&acc)[5])
@@ -452,8 +481,8 @@ __device__ __forceinline__ void eval_item(const EvalCtx &c, long long j, long lo
         r = __shfl_down_sync(0xffffffffu, xt0, 1);
         if (GUARD) {
             if (active) {
-                if (lane == 0) l = fetch_xt(c, 2 * j - 1);
-                if (lane == 31 || j + 1 >= nvec) r = fetch_xt(c, 2 * j + 2);
+                if (lane == 0) l = fetch_xt_p<PEND>(c, 2 * j - 1);
+                if (lane == 31 || j + 1 >= nvec) r = fetch_xt_p<PEND>(c, 2 * j + 2);
             }
         } else {
             const double et = ex + c.alpha * ed; // same two roundings as every other trial value
@@ -488,16 +517,17 @@ __device__ __forceinline__ void eval_item(const EvalCtx &c, long long j, long lo
 }
 
 // odd tail element n-1 (scalar path, one thread)
-template <class OBJ, int MODE>
+template <class OBJ, int MODE, bool PEND = false>
 __device__ __forceinline__ void eval_tail(const EvalCtx &c, const EvalOut &o, double (&acc)[5])
 {
     const long long e = c.n - 1;
-    const double xe = c.x[e], de = c.d[e];
+    const double xe = c.x[e], de = load_d1<PEND>(c, e);
+    if (PEND) c.d_store[e] = de;
     const double xt = xe + c.alpha * de;
     double l = 0.0, r = 0.0;
     if (OBJ::kStencil) {
-        l = fetch_xt(c, e - 1);
-        r = fetch_xt(c, e + 1);
+        l = fetch_xt_p<PEND>(c, e - 1);
+        r = fetch_xt_p<PEND>(c, e + 1);
     }
     const long long G = c.goff + e;
     double ft, gv;
@@ -526,7 +556,7 @@ __device__ __forceinline__ void eval_tail(const EvalCtx &c, const EvalOut &o, do
 // the new iterate is never written over x: it goes to the alternate buffer `xw` (DevState::x_alt)
 // and the scalar kernel swaps the two pointers afterwards.  g IS updated in place: a thread only
 // ever reads the old g of the elements it owns.
-template <class OBJ, int MODE>
+template <class OBJ, int MODE, bool PEND = false>
 __device__ __forceinline__ void eval_run(const EvalCtx &c, const EvalOut &o,
                                          double *__restrict__ partials)
 {
@@ -552,7 +582,7 @@ __device__ __forceinline__ void eval_run(const EvalCtx &c, const EvalOut &o,
                         long long e = lane == 0 ? 2 * j - 1 : (lane == 31 ? 2 * j + 2 : 2 * j);
                         e = (e < 0 || e >= c.n) ? 2 * j : e;
                         ex[u] = c.x[e];
-                        ed[u] = c.d[e];
+                        ed[u] = load_d1<PEND>(c, e);
                     }
                 } else {
 #pragma unroll
@@ -561,13 +591,13 @@ __device__ __forceinline__ void eval_run(const EvalCtx &c, const EvalOut &o,
 #pragma unroll
                 for (int u = 0; u < B; ++u) x2[u] = ld2(c.x, j0 + (ub + u) * kThreads);
 #pragma unroll
-                for (int u = 0; u < B; ++u) d2[u] = ld2(c.d, j0 + (ub + u) * kThreads);
+                for (int u = 0; u < B; ++u) d2[u] = load_d2<PEND>(c, j0 + (ub + u) * kThreads);
 #pragma unroll
                 for (int u = 0; u < B; ++u)
                     go[u] = (MODE == MODE_ACCEPT) ? ld2(o.gw, j0 + (ub + u) * kThreads) : make_double2(0, 0);
 #pragma unroll
                 for (int u = 0; u < B; ++u)
-                    eval_item<OBJ, MODE, false>(c, j0 + (ub + u) * kThreads, 0, true, x2[u], d2[u], go[u], ex[u], ed[u], o, acc);
+                    eval_item<OBJ, MODE, false, PEND>(c, j0 + (ub + u) * kThreads, 0, true, x2[u], d2[u], go[u], ex[u], ed[u], o, acc);
             }
         },
         [&](long long j0, long long nvec) {
@@ -578,13 +608,13 @@ __device__ __forceinline__ void eval_run(const EvalCtx &c, const EvalOut &o,
                 double2 x2 = make_double2(0, 0), d2 = x2, go = x2;
                 if (active) {
                     x2 = ld2(c.x, j);
-                    d2 = ld2(c.d, j);
+                    d2 = load_d2<PEND>(c, j);
                     if (MODE == MODE_ACCEPT) go = ld2(o.gw, j);
                 }
-                eval_item<OBJ, MODE, true>(c, j, nvec, active, x2, d2, go, 0.0, 0.0, o, acc);
+                eval_item<OBJ, MODE, true, PEND>(c, j, nvec, active, x2, d2, go, 0.0, 0.0, o, acc);
             }
         });
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) eval_tail<OBJ, MODE>(c, o, acc);
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) eval_tail<OBJ, MODE, PEND>(c, o, acc);
     constexpr int NQ = (MODE == MODE_TRIAL) ? 3 : 5;
     double v[NQ];
 #pragma unroll
@@ -614,6 +644,7 @@ __device__ __forceinline__ EvalCtx make_ctx(const DevState *st, double alpha)
     c.nglob = st->nglob;
     c.xtL = st->xL + alpha * st->dL;
     c.xtR = st->xR + alpha * st->dR;
+    c.d_store = nullptr;
     return c;
 }
 
@@ -624,9 +655,15 @@ template <class OBJ>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_trial(const DevState *__restrict__ st)
 {
     if (st->ctrl.done || !st->ctrl.ls_active) return;
-    const EvalCtx c = make_ctx(st, st->ls.alpha);
+    EvalCtx c = make_ctx(st, st->ls.alpha);
     const EvalOut o = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    eval_run<OBJ, MODE_TRIAL>(c, o, st->partials);
+    if (st->pend_steepest) { // rare: d = -g on the fly, stored for the later trials and the accept step
+        c.d = st->g;
+        c.d_store = st->w;
+        eval_run<OBJ, MODE_TRIAL, true>(c, o, st->partials);
+    } else {
+        eval_run<OBJ, MODE_TRIAL>(c, o, st->partials);
+    }
 }
 
 // Accept the step alpha = st->ls.alpha (init != 0: alpha = 0 on a zeroed d, i.e. evaluate f, g at x0).
@@ -719,7 +756,7 @@ k_eval_explicit(int mode, int objective, const double *x, const double *d, const
                 double *partials)
 {
     EvalCtx c;
-    c.x = x; c.d = d; c.alpha = *d_alpha; c.n = n; c.goff = 0; c.nglob = n; c.xtL = 0; c.xtR = 0;
+    c.x = x; c.d = d; c.alpha = *d_alpha; c.n = n; c.goff = 0; c.nglob = n; c.xtL = 0; c.xtR = 0; c.d_store = nullptr;
     const EvalOut o = {g_out, x_new, g_io, s_out, y_out};
     if (mode == MODE_TRIAL) eval_dispatch<MODE_TRIAL>(objective, c, o, partials);
     else eval_dispatch<MODE_ACCEPT>(objective, c, o, partials);

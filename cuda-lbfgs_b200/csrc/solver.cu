@@ -18,10 +18,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/lbfgsb200.h"
+#include "accept_gram.cuh"
 #include "comm.h"
 #include "compact.cuh"
 #include "kernels.cuh"
@@ -77,6 +81,63 @@ static int pick_grid(long long n, int sms, int forced, int ctas_per_sm = kCtasPe
     return (int)(tiles < full ? tiles : full);
 }
 
+// ---- device memory: a PRIVATE stream-ordered pool per device --------------------------------------------
+// Solver arenas ((2m+6) vectors, tens of GB) are served from a pool this library creates itself, with the
+// release threshold raised on THAT pool only, so destroying a solver and creating the next one of similar
+// size re-uses the mapping instead of paying cudaMalloc/cudaFree of tens of GB (5-130 ms each way).  The
+// device's default pool -- which torch, NCCL or any other cudaMallocAsync user of the host process shares --
+// is never touched.  Every allocation of the library goes through pool_alloc(), which on an out-of-memory
+// answer hands the cached blocks back to the driver (cudaMemPoolTrimTo) and tries once more;
+// lbfgsb200_trim_memory() does the same on request.
+constexpr int kMaxDevices = 64;
+static cudaMemPool_t g_pools[kMaxDevices] = {};
+static std::mutex g_pool_mutex;
+static int s_optin[kMaxDevices] = {}; // cudaDevAttrMaxSharedMemoryPerBlockOptin per device
+
+static int private_pool(cudaMemPool_t *out)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) { set_error("device ordinal %d out of range", dev); return LBFGSB200_ERR_INVALID; }
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_pools[dev]) {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool;
+        CUDA_TRY(cudaMemPoolCreate(&pool, &props));
+        uint64_t keep = UINT64_MAX;
+        CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        g_pools[dev] = pool;
+    }
+    *out = g_pools[dev];
+    return 0;
+}
+
+// stream-ordered allocation from the private pool; trims the pool and retries once when memory is short
+static int pool_alloc(void **ptr, size_t bytes, cudaStream_t stream)
+{
+    cudaMemPool_t pool;
+    LB_TRY(private_pool(&pool));
+    cudaError_t e = cudaMallocFromPoolAsync(ptr, bytes, pool, stream);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        cudaStreamSynchronize(stream);
+        cudaMemPoolTrimTo(pool, 0);
+        e = cudaMallocFromPoolAsync(ptr, bytes, pool, stream);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *ptr = nullptr;
+        set_error("device allocation of %.3f GB failed: %s", bytes / 1e9, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? LBFGSB200_ERR_NOMEM : LBFGSB200_ERR_CUDA;
+    }
+    return 0;
+}
+
 enum KClass { KC_PASS = 0, KC_TRIAL = 1, KC_ACCEPT = 2, KC_OTHER = 3, KC_GRAM = 4, KC_COMBINE = 5, KC_COUNT = 6 };
 
 } // namespace lb
@@ -90,10 +151,20 @@ struct lbfgsb200_solver {
     int nslots = 0;
     int grid = 1, grid_accept = 1, grid_gram = 1, grid_combine = 1;
     int gram_T = 512;           // compact form: elements per vector per shared-memory tile
-    int gram_tma = 0, gram_NG = 2, gram_NS = 2, gram_G = 1; // pass A: cp.async pipeline (default) or TMA bulk copies
+    int gram_tma = 0, gram_NG = 2, gram_NS = 2, gram_G = 1; // stand-alone pass A: tensor-map TMA (2, default) or cp.async pipeline (0)
     size_t gram_smem = 0;
-    GramMaps *gram_maps = nullptr; // device: tensor maps of the tensor-map TMA variant (gram_tma == 2)
+    ArenaMaps *arena_maps = nullptr; // device: tensor maps over the arena (TMA pass A, fused accept + pass A)
+    ArenaMaps arena_maps_host;       // staging copy (the upload is stream-ordered)
     double *gram = nullptr;     // compact form: Gram matrix + pass-A rows + delta + all-gather buffer
+    // fused compact flow (accept_gram.cuh): k_accept_gram + k_combine_trial
+    bool fused = false;
+    accept_gram_kernel_t ag_kernel = nullptr;
+    combine_trial_kernel_t ct_kernel = nullptr;
+    size_t ag_smem = 0;
+    int grid_ag = 1;
+    int device = 0;
+    void *aux = nullptr;        // ONE allocation for every small device buffer below (partials ... d_st)
+    size_t gram_doubles = 0;
     lbfgsb200_params_t params;
     lbfgsb200_comm *comm = nullptr;
     trial_kernel_t trial_kernel = nullptr;   // objective-specific instantiations
@@ -114,7 +185,10 @@ struct lbfgsb200_solver {
     DevState h_snapshot;        // last state copied back
 
     cudaStream_t stream = nullptr;
+    cudaStream_t capture_stream = nullptr; // graph recording only
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned long long cond_handles[3] = {0, 0, 0}; // WHILE / WHILE / IF handles (DevState::cond_outer, _inner, _fix)
+    int cond_flag = 0;
 
     bool x0_set = false;
     int64_t k_host = 0; // accepts launched so far: an upper bound on the device's h
@@ -158,13 +232,18 @@ struct ClassTimer {
     }
 };
 
+static bool is_multi(const lbfgsb200_solver *s) { return s->comm && s->comm->nranks > 1; }
+
 // scalar step: on one GPU the scalar kernel sums the partials itself; on several the local sums
-// and halo values are packed, all-gathered (one small NCCL call) and summed in rank order.
+// and halo values are packed, exchanged (NVLink mailboxes inside the scalar kernel, or one small NCCL
+// all-gather) and summed in rank order.
 static int scalar_step(lbfgsb200_solver *s, int op, int p, int pack_kind, int nparts_override = -1)
 {
-    const int nparts = nparts_override >= 0 ? nparts_override : (op == OP_ACCEPT || op == OP_INIT) ? s->grid_accept : (op == OP_COMPACT_DIR ? s->grid_combine : s->grid);
-    const bool needs_data = (op != OP_ITER_BEGIN && op != OP_LS_INIT);
-    if (s->comm && s->comm->nranks > 1 && needs_data) {
+    const int nparts = nparts_override >= 0 ? nparts_override
+                       : (op == OP_ACCEPT || op == OP_INIT) ? s->grid_accept
+                       : (op == OP_COMPACT_DIR || op == OP_F_DIR) ? s->grid_combine : s->grid;
+    const bool needs_data = (op != OP_ITER_BEGIN && op != OP_LS_INIT && op != OP_F_BEGIN);
+    if (is_multi(s) && needs_data) {
         if (s->comm->p2p) {
             // pack + NVLink mailbox exchange + scalar logic fused in ONE kernel (scalar_ops.cuh)
             k_scalar<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, op, p, 2, pack_kind, nparts);
@@ -182,7 +261,47 @@ static int scalar_step(lbfgsb200_solver *s, int op, int p, int pack_kind, int np
     return 0;
 }
 
-// search direction: seq/lbfgs.cpp:86-153
+// the stand-alone pass A (old compact flow; fused flow: only after a rejected pair with a full ring)
+static void launch_gram(lbfgsb200_solver *s)
+{
+    const int m = s->params.m;
+    const size_t smem = s->gram_smem;
+    if (s->gram_tma == 2) {
+        if ((2 * m + 1 + s->gram_NG - 1) / s->gram_NG <= 7)
+            k_gram_tma2d<7><<<s->grid_gram, kWsThreads, smem, s->stream>>>(s->d_st, s->arena_maps, s->gram_T, s->gram_NG);
+        else
+            k_gram_tma2d<kMaxCW><<<s->grid_gram, kWsThreads, smem, s->stream>>>(s->d_st, s->arena_maps, s->gram_T, s->gram_NG);
+    } else {
+        const int G = s->gram_G, per = (2 * m + 1 + G - 1) / G, cwg = (per + kGramWarps - 1) / kGramWarps;
+        const dim3 grid(s->grid_gram, G);
+        if (cwg <= 3) k_gram<3><<<grid, kThreads, smem, s->stream>>>(s->d_st, s->gram_T, s->gram_NS, G);
+        else if (cwg <= 6) k_gram<6><<<grid, kThreads, smem, s->stream>>>(s->d_st, s->gram_T, s->gram_NS, G);
+        else k_gram<kMaxCW><<<grid, kThreads, smem, s->stream>>>(s->d_st, s->gram_T, s->gram_NS, G);
+    }
+    s->launches += 1;
+}
+
+// scalar kernel of the compact ops that carry pass-A rows (OP_COMPACT, OP_F_INIT, OP_F_ACCEPT, OP_F_FIX): dynamic
+// shared memory = the (2m+1)^2 window Gram matrix of the coefficient recursion
+static int rows_step(lbfgsb200_solver *s, int op, int nparts)
+{
+    const int J = 2 * s->params.m + 1;
+    const size_t dyn = sizeof(double) * (size_t)J * J;
+    const bool multi = is_multi(s), p2p = multi && s->comm->p2p;
+    if (multi && !p2p) {
+        // NCCL path: the rows must be in HBM for the all-gather (otherwise the scalar kernel sums them itself)
+        if (op == OP_COMPACT) k_gram_finalize<<<3 * J, kScalarThreads, 0, s->stream>>>(s->d_st, nparts);
+        else k_pack_rows<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, op, nparts);
+        s->launches += 1;
+        LB_TRY(comm_allgather(s->comm, s->h_snapshot.gram_rows, s->h_snapshot.gram_recv, s->h_snapshot.gram_count, s->stream));
+    }
+    k_scalar<<<1, kScalarThreads, dyn, s->stream>>>(s->d_st, op, 0, p2p ? 2 : (multi ? 1 : 0), PACK_NONE, nparts);
+    s->launches += 1;
+    return 0;
+}
+
+// search direction: seq/lbfgs.cpp:86-153 (explicit two-loop recursion, or the UNFUSED compact form, which user
+// objectives still run on; built-in objectives with direction = compact take the fused flow below)
 static int launch_direction(lbfgsb200_solver *s)
 {
     const int m = s->params.m;
@@ -190,43 +309,11 @@ static int launch_direction(lbfgsb200_solver *s)
     LB_TRY(scalar_step(s, OP_ITER_BEGIN, 0, PACK_NONE));
     if (h_upper > 0 && s->params.direction == LBFGSB200_DIR_COMPACT) {
         // compact form: pass A (Gram rows) -> coefficient recursion -> pass B (combine)
-        const int J = 2 * h_upper + 1;
         {
             ClassTimer t(s, KC_GRAM);
-            const size_t smem = s->gram_smem;
-            if (s->gram_tma == 2) {
-                if ((2 * m + 1 + s->gram_NG - 1) / s->gram_NG <= 7)
-                    k_gram_tma2d<7><<<s->grid_gram, kWsThreads, smem, s->stream>>>(s->d_st, s->gram_maps, s->gram_T, s->gram_NG);
-                else
-                    k_gram_tma2d<kMaxCW><<<s->grid_gram, kWsThreads, smem, s->stream>>>(s->d_st, s->gram_maps, s->gram_T, s->gram_NG);
-            } else if (s->gram_tma) {
-                if ((2 * m + 1 + s->gram_NG - 1) / s->gram_NG <= 7)
-                    k_gram_tma<7><<<s->grid_gram, kWsThreads, smem, s->stream>>>(s->d_st, s->gram_T, s->gram_NG);
-                else
-                    k_gram_tma<kMaxCW><<<s->grid_gram, kWsThreads, smem, s->stream>>>(s->d_st, s->gram_T, s->gram_NG);
-            } else {
-                const int G = s->gram_G, per = (2 * m + 1 + G - 1) / G, cwg = (per + kGramWarps - 1) / kGramWarps;
-                const dim3 grid(s->grid_gram, G);
-                if (cwg <= 3) k_gram<3><<<grid, kThreads, smem, s->stream>>>(s->d_st, s->gram_T, s->gram_NS, G);
-                else if (cwg <= 6) k_gram<6><<<grid, kThreads, smem, s->stream>>>(s->d_st, s->gram_T, s->gram_NS, G);
-                else k_gram<kMaxCW><<<grid, kThreads, smem, s->stream>>>(s->d_st, s->gram_T, s->gram_NS, G);
-            }
-            s->launches += 1;
+            launch_gram(s);
         }
-        const bool multi = s->comm && s->comm->nranks > 1;
-        const bool p2p = multi && s->comm->p2p;
-        if (multi && !p2p) {
-            // NCCL path: the rows must be in HBM for the all-gather (otherwise the scalar kernel sums them itself)
-            k_gram_finalize<<<3 * J, kScalarThreads, 0, s->stream>>>(s->d_st, s->grid_gram);
-            s->launches += 1;
-            const int cnt = 3 * (2 * m + 1);
-            double *rows = s->h_snapshot.gram_rows;
-            LB_TRY(comm_allgather(s->comm, rows, s->h_snapshot.gram_recv, cnt, s->stream));
-        }
-        // dynamic shared memory: the (2h+1)^2 window Gram matrix of the coefficient recursion
-        k_scalar<<<1, kScalarThreads, sizeof(double) * (size_t)J * J, s->stream>>>(s->d_st, OP_COMPACT, 0, p2p ? 2 : (multi ? 1 : 0),
-                                                                                   PACK_NONE, s->grid_gram);
-        s->launches += 1;
+        LB_TRY(rows_step(s, OP_COMPACT, s->grid_gram));
         {
             ClassTimer t(s, KC_COMBINE);
             k_combine<<<s->grid_combine, kThreads, 0, s->stream>>>(s->d_st);
@@ -279,6 +366,7 @@ static int snapshot(lbfgsb200_solver *s)
     CUDA_TRY(cudaMemcpyAsync(&s->h_snapshot, s->d_st, sizeof(DevState), cudaMemcpyDeviceToHost,
                              s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    *s->h_ctrl = s->h_snapshot.ctrl;
     return 0;
 }
 
@@ -310,6 +398,70 @@ static int run_stepped(lbfgsb200_solver *s, int64_t iterations)
     return 0;
 }
 
+// ---- fused compact flow (accept_gram.cuh) ---------------------------------------------------------
+//   [ stand-alone pass A + OP_F_FIX, only after a rejected pair with a full ring ]
+//   k_combine_trial (d, g.d, first trial)      -> OP_F_DIR    (safeguard, search start, first decision)
+//   { k_trial -> OP_LS_STEP }                   further trials, if the search wants them
+//   k_accept_gram (accept + next pass A)       -> OP_F_ACCEPT (bookkeeping, Gram update, next coefficients)
+static void launch_accept_gram(lbfgsb200_solver *s, int init)
+{
+    ClassTimer t(s, KC_GRAM);
+    s->ag_kernel<<<s->grid_ag, kWsThreads, s->ag_smem, s->stream>>>(s->d_st, s->arena_maps, s->gram_T, s->gram_NG, init);
+    s->launches += 1;
+}
+
+static int fused_fix_segment(lbfgsb200_solver *s)
+{
+    launch_gram(s);
+    return rows_step(s, OP_F_FIX, s->grid_gram);
+}
+
+static int fused_direction_segment(lbfgsb200_solver *s)
+{
+    {
+        ClassTimer t(s, KC_COMBINE);
+        s->ct_kernel<<<s->grid_combine, kThreads, 0, s->stream>>>(s->d_st);
+        s->launches += 1;
+    }
+    return scalar_step(s, OP_F_DIR, 0, PACK_NONE);
+}
+
+static int fused_trial_segment(lbfgsb200_solver *s)
+{
+    {
+        ClassTimer t(s, KC_TRIAL);
+        s->trial_kernel<<<s->grid, kThreads, 0, s->stream>>>(s->d_st);
+        s->launches += 1;
+    }
+    return scalar_step(s, OP_LS_STEP, 0, PACK_NONE);
+}
+
+static int fused_accept_segment(lbfgsb200_solver *s, int init)
+{
+    launch_accept_gram(s, init);
+    return rows_step(s, init ? OP_F_INIT : OP_F_ACCEPT, s->grid_ag);
+}
+
+static int run_stepped_fused(lbfgsb200_solver *s, int64_t iterations)
+{
+    // s->h_ctrl is current: set_x0 / the previous run ended with a snapshot
+    for (int64_t it = 0; it < iterations && !s->h_ctrl->done; ++it) {
+        if (s->h_ctrl->need_fix) LB_TRY(fused_fix_segment(s));
+        LB_TRY(fused_direction_segment(s));
+        LB_TRY(read_ctrl(s));
+        while (s->h_ctrl->ls_active && !s->h_ctrl->done) {
+            LB_TRY(fused_trial_segment(s));
+            LB_TRY(read_ctrl(s));
+        }
+        if (s->h_ctrl->done) break;
+        LB_TRY(fused_accept_segment(s, 0));
+        LB_TRY(read_ctrl(s));
+        s->k_host += 1;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // ---- graph mode -------------------------------------------------------------------------------
 // One CUDA graph = the whole solve.  Its single top-level node is a WHILE node (condition: not
 // done and iteration budget left) whose body is one L-BFGS iteration: the direction phase, a
@@ -325,11 +477,19 @@ static int run_stepped(lbfgsb200_solver *s, int64_t iterations)
         }                                                                                     \
     } while (0)
 
+// The graph is recorded on a stream of its own: the solver stream may still be busy (the upload of x0), and
+// recording does not execute anything.
 template <class F>
 static int capture_segment(lbfgsb200_solver *s, cudaGraph_t g, std::vector<cudaGraphNode_t> &tail, F &&body)
 {
-    GRAPH_TRY(cudaStreamBeginCaptureToGraph(s->stream, g, tail.empty() ? nullptr : tail.data(), nullptr, tail.size(),
-                                            cudaStreamCaptureModeThreadLocal));
+    cudaStream_t run_stream = s->stream;
+    s->stream = s->capture_stream;
+    cudaError_t e0 = cudaStreamBeginCaptureToGraph(s->stream, g, tail.empty() ? nullptr : tail.data(), nullptr, tail.size(),
+                                                   cudaStreamCaptureModeThreadLocal);
+    if (e0 != cudaSuccess) {
+        s->stream = run_stream;
+        GRAPH_TRY(e0);
+    }
     int rc = body();
     cudaStreamCaptureStatus status;
     const cudaGraphNode_t *deps = nullptr;
@@ -338,19 +498,20 @@ static int capture_segment(lbfgsb200_solver *s, cudaGraph_t g, std::vector<cudaG
     if (e == cudaSuccess) tail.assign(deps, deps + ndeps);
     cudaGraph_t out = nullptr;
     cudaError_t e2 = cudaStreamEndCapture(s->stream, &out);
+    s->stream = run_stream;
     if (rc < 0) return rc;
     GRAPH_TRY(e);
     GRAPH_TRY(e2);
     return 0;
 }
 
-static int add_while(cudaGraph_t parent, std::vector<cudaGraphNode_t> &tail, cudaGraphConditionalHandle h,
-                     cudaGraph_t *body)
+static int add_conditional(cudaGraph_t parent, std::vector<cudaGraphNode_t> &tail, cudaGraphConditionalHandle h,
+                           cudaGraphConditionalNodeType type, cudaGraph_t *body)
 {
     cudaGraphNodeParams p = {};
     p.type = cudaGraphNodeTypeConditional;
     p.conditional.handle = h;
-    p.conditional.type = cudaGraphCondTypeWhile;
+    p.conditional.type = type;
     p.conditional.size = 1;
     cudaGraphNode_t node;
     GRAPH_TRY(cudaGraphAddNode(&node, parent, tail.empty() ? nullptr : tail.data(), tail.size(), &p));
@@ -362,48 +523,73 @@ static int add_while(cudaGraph_t parent, std::vector<cudaGraphNode_t> &tail, cud
 static int build_graph(lbfgsb200_solver *s)
 {
     GRAPH_TRY(cudaGraphCreate(&s->graph, 0));
-    cudaGraphConditionalHandle h_outer, h_inner;
-    GRAPH_TRY(cudaGraphConditionalHandleCreate(&h_outer, s->graph, 1, cudaGraphCondAssignDefault));
-    GRAPH_TRY(cudaGraphConditionalHandleCreate(&h_inner, s->graph, 0, 0));
+    cudaGraphConditionalHandle h_outer, h_inner, h_fix = 0;
+    if (s->fused) {
+        // every condition is armed by the prologue kernel / the scalar kernels from the device state
+        GRAPH_TRY(cudaGraphConditionalHandleCreate(&h_outer, s->graph, 0, 0));
+        GRAPH_TRY(cudaGraphConditionalHandleCreate(&h_inner, s->graph, 0, 0));
+        GRAPH_TRY(cudaGraphConditionalHandleCreate(&h_fix, s->graph, 0, 0));
+    } else {
+        GRAPH_TRY(cudaGraphConditionalHandleCreate(&h_outer, s->graph, 1, cudaGraphCondAssignDefault));
+        GRAPH_TRY(cudaGraphConditionalHandleCreate(&h_inner, s->graph, 0, 0));
+    }
     s->h_snapshot.cond_outer = h_outer;
     s->h_snapshot.cond_inner = h_inner;
-    s->h_snapshot.use_graph = 1;
-    CUDA_TRY(cudaMemcpyAsync(&s->d_st->cond_outer, &s->h_snapshot.cond_outer, sizeof h_outer, cudaMemcpyHostToDevice, s->stream));
-    CUDA_TRY(cudaMemcpyAsync(&s->d_st->cond_inner, &s->h_snapshot.cond_inner, sizeof h_inner, cudaMemcpyHostToDevice, s->stream));
-    CUDA_TRY(cudaMemcpyAsync(&s->d_st->use_graph, &s->h_snapshot.use_graph, sizeof(int), cudaMemcpyHostToDevice, s->stream));
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    s->h_snapshot.cond_fix = h_fix;
+    s->cond_handles[0] = h_outer;
+    s->cond_handles[1] = h_inner;
+    s->cond_handles[2] = h_fix; // uploaded (stream-ordered) by do_iterate before every launch
 
     std::vector<cudaGraphNode_t> top_tail, tail;
     cudaGraph_t iter_body = nullptr, trial_body = nullptr;
-    LB_TRY(add_while(s->graph, top_tail, h_outer, &iter_body));
     const int64_t k_saved = s->k_host, l_saved = s->launches;
-    s->k_host = s->params.m; // capture the passes of all m window positions; unused ones exit at once
-    LB_TRY(capture_segment(s, iter_body, tail, [&]() { return launch_direction(s); }));
-    LB_TRY(add_while(iter_body, tail, h_inner, &trial_body));
-    std::vector<cudaGraphNode_t> inner_tail;
-    LB_TRY(capture_segment(s, trial_body, inner_tail, [&]() {
-        s->trial_kernel<<<s->grid, kThreads, 0, s->stream>>>(s->d_st);
-        return scalar_step(s, OP_LS_STEP, 0, PACK_NONE);
-    }));
-    const int64_t after_inner = s->launches;
-    LB_TRY(capture_segment(s, iter_body, tail, [&]() {
-        s->accept_kernel<<<s->grid_accept, kThreads, 0, s->stream>>>(s->d_st, 0);
-        s->launches += 1;
-        return scalar_step(s, OP_ACCEPT, 0, PACK_ACCEPT);
-    }));
-    (void)after_inner;
-    // fixed part = everything captured except the two nodes of the trial loop body
-    s->graph_fixed_launches = (s->launches - l_saved) - 1; // scalar_step of the trial body counted once; k_trial not counted
+    if (s->fused) {
+        LB_TRY(capture_segment(s, s->graph, top_tail, [&]() { return scalar_step(s, OP_F_BEGIN, 0, PACK_NONE); }));
+        LB_TRY(add_conditional(s->graph, top_tail, h_outer, cudaGraphCondTypeWhile, &iter_body));
+        cudaGraph_t fix_body = nullptr;
+        LB_TRY(add_conditional(iter_body, tail, h_fix, cudaGraphCondTypeIf, &fix_body));
+        std::vector<cudaGraphNode_t> fix_tail;
+        LB_TRY(capture_segment(s, fix_body, fix_tail, [&]() { return fused_fix_segment(s); }));
+        LB_TRY(capture_segment(s, iter_body, tail, [&]() { return fused_direction_segment(s); }));
+        LB_TRY(add_conditional(iter_body, tail, h_inner, cudaGraphCondTypeWhile, &trial_body));
+        std::vector<cudaGraphNode_t> inner_tail;
+        LB_TRY(capture_segment(s, trial_body, inner_tail, [&]() { return fused_trial_segment(s); }));
+        LB_TRY(capture_segment(s, iter_body, tail, [&]() { return fused_accept_segment(s, 0); }));
+        s->graph_fixed_launches = 4; // combine + OP_F_DIR + accept_gram + OP_F_ACCEPT ; + 2 per further trial
+    } else {
+        LB_TRY(add_conditional(s->graph, top_tail, h_outer, cudaGraphCondTypeWhile, &iter_body));
+        s->k_host = s->params.m; // capture the passes of all m window positions; unused ones exit at once
+        LB_TRY(capture_segment(s, iter_body, tail, [&]() { return launch_direction(s); }));
+        LB_TRY(add_conditional(iter_body, tail, h_inner, cudaGraphCondTypeWhile, &trial_body));
+        std::vector<cudaGraphNode_t> inner_tail;
+        LB_TRY(capture_segment(s, trial_body, inner_tail, [&]() {
+            s->trial_kernel<<<s->grid, kThreads, 0, s->stream>>>(s->d_st);
+            return scalar_step(s, OP_LS_STEP, 0, PACK_NONE);
+        }));
+        LB_TRY(capture_segment(s, iter_body, tail, [&]() {
+            s->accept_kernel<<<s->grid_accept, kThreads, 0, s->stream>>>(s->d_st, 0);
+            s->launches += 1;
+            return scalar_step(s, OP_ACCEPT, 0, PACK_ACCEPT);
+        }));
+        // fixed part = everything captured except the two nodes of the trial loop body
+        s->graph_fixed_launches = (s->launches - l_saved) - 1; // scalar_step of the trial body counted once; k_trial not counted
+    }
     s->k_host = k_saved;
     s->launches = l_saved;
     GRAPH_TRY(cudaGraphInstantiate(&s->graph_exec, s->graph, 0));
     return 0;
 }
 
+static bool wants_graph(const lbfgsb200_solver *s)
+{
+    // graph mode: not instrumented, no user callbacks, and on several GPUs only with the peer-to-peer exchange,
+    // whose kernels are ordinary graph nodes (NCCL calls and event pairs stay on the stepped path)
+    return s->params.use_graph && !s->profiling && !s->cb && !(is_multi(s) && !s->comm->p2p);
+}
+
 static int run_graph(lbfgsb200_solver *s, int64_t iterations)
 {
     if (iterations <= 0) return 0;
-    if (!s->graph_exec) LB_TRY(build_graph(s));
     long long budget = iterations;
     CUDA_TRY(cudaMemcpyAsync(&s->d_st->iters_left, &budget, sizeof budget, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaGraphLaunch(s->graph_exec, s->stream));
@@ -450,26 +636,34 @@ static int do_iterate(lbfgsb200_solver *s, int64_t iterations)
         return LBFGSB200_ERR_INVALID;
     }
     s->streams_at_start = s->h_snapshot.vec_streams;
-    // graph mode: single GPU, not instrumented (NCCL calls and event pairs stay on the stepped path)
-    // (multi-GPU: only with the peer-to-peer exchange, whose kernels are ordinary graph nodes)
-    const bool graph = s->params.use_graph && !s->profiling && !s->cb && !(s->comm && s->comm->nranks > 1 && !s->comm->p2p);
+    const bool graph = wants_graph(s);
     if (graph && !s->graph_exec) LB_TRY(build_graph(s));
     if (s->graph_exec) { // cudaGraphSetConditional is only legal inside the graph: gate it per run
-        const int flag = graph ? 1 : 0;
-        CUDA_TRY(cudaMemcpyAsync(&s->d_st->use_graph, &flag, sizeof flag, cudaMemcpyHostToDevice, s->stream));
+        s->cond_flag = graph ? 1 : 0;
+        CUDA_TRY(cudaMemcpyAsync(&s->d_st->cond_outer, s->cond_handles, sizeof s->cond_handles, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(&s->d_st->use_graph, &s->cond_flag, sizeof(int), cudaMemcpyHostToDevice, s->stream));
     }
     const long long k0 = s->h_snapshot.k, t0 = s->h_snapshot.trial_evals;
+    const bool was_done = s->h_snapshot.ctrl.done != 0;
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
-    int rc = graph ? run_graph(s, iterations) : (s->cb ? run_stepped_callback(s, iterations) : run_stepped(s, iterations));
+    int rc = graph ? run_graph(s, iterations)
+                   : (s->cb ? run_stepped_callback(s, iterations) : (s->fused ? run_stepped_fused(s, iterations) : run_stepped(s, iterations)));
     CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
     if (rc < 0) return rc;
     LB_TRY(snapshot(s));
-    if (graph) { // kernel nodes executed: fixed part per iteration + 2 per trial
+    if (graph && iterations > 0) { // kernel nodes executed: fixed part per iteration + 2 per stand-alone trial
         const long long its = s->h_snapshot.k - k0, trials = s->h_snapshot.trial_evals - t0;
-        // an exit at the top of / inside an iteration (converged, line search failed) still ran that
-        // iteration's nodes as no-ops; "maximum iterations" is raised by the last accept itself
-        const bool extra = s->h_snapshot.ctrl.done && s->h_snapshot.status != LBFGSB200_MAX_ITER;
-        s->launches += (its + (extra ? 1 : 0)) * s->graph_fixed_launches + 2 * trials;
+        if (s->fused) {
+            // prologue + per iteration {combine, OP_F_DIR, accept_gram, OP_F_ACCEPT} + 2 per trial beyond the fused first
+            // one; an iteration whose search failed ran its direction segment but no accept
+            const bool ls_failed_now = !was_done && s->h_snapshot.status == LBFGSB200_LS_FAILED;
+            s->launches += 1 + its * s->graph_fixed_launches + 2 * (trials - its - (ls_failed_now ? 1 : 0)) + (ls_failed_now ? 2 : 0);
+        } else {
+            // an exit at the top of / inside an iteration (converged, line search failed) still ran that
+            // iteration's nodes as no-ops; "maximum iterations" is raised by the last accept itself
+            const bool extra = s->h_snapshot.ctrl.done && s->h_snapshot.status != LBFGSB200_MAX_ITER;
+            s->launches += (its + (extra ? 1 : 0)) * s->graph_fixed_launches + 2 * trials;
+        }
         s->k_host += its;
     }
     float ms = 0.f;
@@ -525,7 +719,10 @@ int lbfgsb200_params_default(lbfgsb200_params_t *p, int flavor)
     p->line_search = LBFGSB200_LS_BACKTRACKING;
     p->flavor = flavor;
     p->profile = LBFGSB200_PROFILE_SEQ;
-    p->direction = LBFGSB200_DIR_TWO_LOOP;
+    // the fast path is the default: compact (Gram) direction in the fused two-kernel flow, whole solve as one
+    // CUDA graph.  Parity with the reference is pinned for it at every size the reference is quoted on
+    // (tests/test_gpu_large.py); m > 50 needs direction = LBFGSB200_DIR_TWO_LOOP.
+    p->direction = LBFGSB200_DIR_AUTO;
     p->c1 = 1e-4;                                         // seq/config.h:5, par/constants.h:5
     p->c2 = (flavor != LBFGSB200_FLAVOR_SEQ) ? 0.7 : 0.9; // par/constants.h:6 / seq/config.h:6
     p->step0 = 1.0;                                       // INITIAL_STEP_SIZE
@@ -533,9 +730,10 @@ int lbfgsb200_params_default(lbfgsb200_params_t *p, int flavor)
     p->backtracking_tol = (flavor == LBFGSB200_FLAVOR_PAR_INLINED) ? 1e-10 : 1e-8; // BACKTRACKING_TOL (par/L-BFGS-Backtracking.cu:155)
     p->wolfe_min = 1e-10;                                 // WOLFE_INTERP_MIN
     p->ls_max_trials = 20;
-    p->use_graph = 0;
+    p->use_graph = 1;
     p->verbose = 0;
     p->grid_ctas = 0;
+    p->num_gpus = 0; // lbfgsb200_solve: as many visible GPUs as the problem size warrants (see lbfgsb200.h)
     return 0;
 }
 
@@ -551,44 +749,46 @@ void lbfgsb200_shard_range(size_t n_global, int rank, int nranks, size_t *offset
     if (n_local) *n_local = len;
 }
 
-// Tensor maps for the tensor-map TMA variant of pass A: S and Y are [nslots][stride] row-major FP64
-// tensors; one map per run length r (box = T columns x r rows), plus a 1-row map over g.
+// Tensor maps over the arena (compact.cuh, ArenaMaps): a row-major [4 + 2 nslots][stride] FP64 tensor; one map per
+// run length r (box = T columns x r rows) plus the 2-column halo box of the fused accept kernel.
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int build_gram_maps(lbfgsb200_solver *s, const DevState &st)
+static int build_arena_maps(lbfgsb200_solver *s, ArenaMaps *dev_dst)
 {
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
-        qres != cudaDriverEntryPointSuccess) {
-        set_error("cuTensorMapEncodeTiled is not available");
-        cudaGetLastError();
-        return LBFGSB200_ERR_CUDA;
+    static encode_tiled_fn encode = nullptr; // the entry point is process-wide
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+            qres != cudaDriverEntryPointSuccess) {
+            set_error("cuTensorMapEncodeTiled is not available");
+            cudaGetLastError();
+            return LBFGSB200_ERR_CUDA;
+        }
+        encode = (encode_tiled_fn)fn;
     }
-    encode_tiled_fn encode = (encode_tiled_fn)fn;
-    GramMaps *host = new GramMaps;
+    const int rows_total = 4 + 2 * s->nslots;
+    ArenaMaps *host = &s->arena_maps_host;
     memset(host, 0, sizeof *host);
-    auto make = [&](CUtensorMap *out, double *base, int rows_total, int box_rows) -> bool {
+    auto make = [&](CUtensorMap *out, int box_cols, int box_rows) -> bool {
         const cuuint64_t gdim[2] = {(cuuint64_t)s->stride, (cuuint64_t)rows_total};
         const cuuint64_t gstride[1] = {(cuuint64_t)s->stride * sizeof(double)};
-        const cuuint32_t box[2] = {(cuuint32_t)s->gram_T, (cuuint32_t)box_rows};
+        const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
         const cuuint32_t estr[2] = {1, 1};
-        CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, s->arena, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) set_error("cuTensorMapEncodeTiled failed with %d (rows %d, box %d x %d)", (int)r, rows_total, s->gram_T, box_rows);
+        if (r != CUDA_SUCCESS) set_error("cuTensorMapEncodeTiled failed with %d (rows %d, box %d x %d)", (int)r, rows_total, box_cols, box_rows);
         return r == CUDA_SUCCESS;
     };
     bool ok = true;
-    for (int r = 1; r <= s->nslots && ok; ++r) ok = make(&host->s[r], st.S, s->nslots, r) && make(&host->y[r], st.Y, s->nslots, r);
-    ok = ok && make(&host->g, st.g, 1, 1);
-    int rc = 0;
-    if (!ok) rc = LBFGSB200_ERR_CUDA;
-    if (!rc && cudaMalloc(&s->gram_maps, sizeof(GramMaps)) != cudaSuccess) rc = LBFGSB200_ERR_NOMEM;
-    if (!rc && cudaMemcpy(s->gram_maps, host, sizeof(GramMaps), cudaMemcpyHostToDevice) != cudaSuccess) rc = LBFGSB200_ERR_CUDA;
-    delete host;
-    return rc;
+    for (int r = 1; r <= s->nslots && ok; ++r) ok = make(&host->run[r], s->gram_T, r);
+    ok = ok && make(&host->halo, 2, 1);
+    if (!ok) return LBFGSB200_ERR_CUDA;
+    // (the host copy lives in the solver: the upload is stream-ordered)
+    CUDA_TRY(cudaMemcpyAsync(dev_dst, host, sizeof(ArenaMaps), cudaMemcpyHostToDevice, s->stream));
+    return 0;
 }
 
 static int check_params(const lbfgsb200_params_t *p)
@@ -601,13 +801,50 @@ static int check_params(const lbfgsb200_params_t *p)
         return LBFGSB200_ERR_INVALID;
     }
     if (p->flavor < 0 || p->flavor > 2 || p->profile < 0 || p->profile > 1 || p->direction < 0 ||
-        p->direction > 1) {
+        p->direction > 2) {
         set_error("bad flavor/profile/direction");
         return LBFGSB200_ERR_INVALID;
     }
     if (p->direction == LBFGSB200_DIR_COMPACT && p->m > kMaxCompactM) { set_error("compact direction supports m <= %d", kMaxCompactM); return LBFGSB200_ERR_INVALID; }
     if (p->max_iterations < 0 || p->ls_max_trials < 1) { set_error("bad iteration limits"); return LBFGSB200_ERR_INVALID; }
+    // The trial loops run on the device (in graph mode the host cannot interrupt them): refuse constants with which
+    // a search would never end (the backtracking loops stop when alpha * shrink^k drops below backtracking_tol).
+    if (!(p->shrink > 0.0 && p->shrink < 1.0)) { set_error("shrink=%g must lie in (0, 1)", p->shrink); return LBFGSB200_ERR_INVALID; }
+    if (!(p->step0 > 0.0) || !isfinite(p->step0)) { set_error("step0=%g must be positive and finite", p->step0); return LBFGSB200_ERR_INVALID; }
+    if (!(p->backtracking_tol > 0.0) || !(p->wolfe_min > 0.0)) { set_error("backtracking_tol and wolfe_min must be positive"); return LBFGSB200_ERR_INVALID; }
+    if (!(p->c1 > 0.0) || !(p->c2 > 0.0) || !isfinite(p->c1) || !isfinite(p->c2)) { set_error("c1 and c2 must be positive and finite"); return LBFGSB200_ERR_INVALID; }
+    if (!(p->tolerance >= 0.0)) { set_error("tolerance=%g must be >= 0", p->tolerance); return LBFGSB200_ERR_INVALID; }
+    if (log(p->backtracking_tol / p->step0) / log(p->shrink) > 1e5) { set_error("shrink=%g needs more than 1e5 backtracking trials to reach backtracking_tol", p->shrink); return LBFGSB200_ERR_INVALID; }
+    if (p->num_gpus < 0 || p->num_gpus > kMaxRanks) { set_error("num_gpus=%d out of range 0..%d", p->num_gpus, kMaxRanks); return LBFGSB200_ERR_INVALID; }
     return 0;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// one pinned 64-byte control block per solver, recycled through a process-wide free list (cudaHostAlloc /
+// cudaFreeHost cost ~0.5 ms each and synchronise the device)
+static std::vector<void *> g_pinned_free;
+static void *pinned_block_get()
+{
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        if (!g_pinned_free.empty()) {
+            void *p = g_pinned_free.back();
+            g_pinned_free.pop_back();
+            return p;
+        }
+    }
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, 64, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+static void pinned_block_put(void *p)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    g_pinned_free.push_back(p);
 }
 
 int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
@@ -625,6 +862,9 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     lbfgsb200_solver *s = new (std::nothrow) lbfgsb200_solver;
     if (!s) return LBFGSB200_ERR_NOMEM;
     s->params = *params;
+    if (s->params.direction == LBFGSB200_DIR_AUTO)
+        s->params.direction = params->m <= kMaxCompactM ? LBFGSB200_DIR_COMPACT : LBFGSB200_DIR_TWO_LOOP;
+    params = &s->params;
     s->objective = objective;
     s->trial_kernel = trial_kernel_for(objective);
     s->accept_kernel = accept_kernel_for(objective);
@@ -638,29 +878,33 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     s->stride = (s->n_local + 31) / 32 * 32; // 256-byte rows
     int rc = sm_count(&s->sms);
     if (rc < 0) { delete s; return rc; }
+    cudaGetDevice(&s->device);
     s->grid = pick_grid((long long)s->n_local, s->sms, params->grid_ctas);
     s->grid_accept = pick_grid((long long)s->n_local, s->sms, params->grid_ctas, kCtasPerSmAccept);
-    if (params->direction == LBFGSB200_DIR_COMPACT) {
-        // shared-memory tile of all 2m+1 basis vectors; keep two CTAs per SM resident
-        const int J = 2 * params->m + 1;
-        // Three implementations of pass A, picked by history size, LBFGSB200_GRAM_TMA forces one:
-        //   2  tensor-map TMA (UTMALDG.2D): <= 5 tiled loads per tile of the whole history.  Default for
-        //      m > 6: 7.0-7.3 TB/s at m = 10..50 (1.07-1.11x the measured copy peak)
-        //   1  one-row bulk copies (UBLKCP), tiles of 512 elements.  Default for m <= 6: 6.8-7.2 TB/s
-        //   0  cp.async (LDGSTS) pipeline with column groups: 6.1-6.9 TB/s; fallback when the tensor maps
-        //      cannot be built (shards of 2^31 elements or more: TMA coordinates are 32-bit)
+    const bool compact = params->direction == LBFGSB200_DIR_COMPACT;
+    const int J = 2 * params->m + 1;
+    if (compact) {
+        // Pass A, stand-alone (user objectives; fused flow: only after a rejected pair), LBFGSB200_GRAM_TMA forces one:
+        //   2  tensor-map TMA (UTMALDG.2D): <= 5 tiled loads per tile of the whole history (default)
+        //   0  cp.async (LDGSTS) pipeline with column groups: the fallback when the tensor maps cannot be used
+        //      (shards of 2^31 elements or more: TMA coordinates are 32-bit)
+        // The fused flow (k_accept_gram / k_combine_trial, LBFGSB200_FUSED=0 disables it) needs the tensor maps.
         const char *env = getenv("LBFGSB200_GRAM_TMA");
-        s->gram_tma = env ? atoi(env) : (params->m <= 6 ? 1 : 2);
-        if (s->gram_tma == 2 && s->stride >= ((size_t)1 << 31)) s->gram_tma = 0;
+        s->gram_tma = env ? (atoi(env) ? 2 : 0) : 2;
+        if (s->stride >= ((size_t)1 << 31)) s->gram_tma = 0;
+        const char *ef = getenv("LBFGSB200_FUSED");
+        s->fused = s->gram_tma == 2 && objective != LBFGSB200_OBJ_DEVICE_CALLBACK && !(ef && atoi(ef) == 0);
         int Jt = J;
         if (s->gram_tma) {
-            // TMA variant: ONE CTA per SM owning (almost) all of shared memory: kGramStages stages of the
-            // largest tile that fits ~200 KB, so kGramStages-1 whole tiles per SM are in flight
+            // ONE CTA per SM owning (almost) all of shared memory: kGramStages stages of the largest tile that
+            // fits, so kGramStages-1 whole tiles per SM are in flight.  The fused kernel's stage carries 3 more rows
+            // (x, d, g_old inputs next to the s, y, g_new it forms) and the halo slots; both kernels share T.
             const char *eb = getenv("LBFGSB200_GRAM_TMA_KB");
             const size_t budget = (size_t)(eb ? atoi(eb) : 216) * 1024;
             s->gram_NS = kGramStages;
-            s->gram_T = s->gram_tma == 2 ? 256 : 512; // a TMA box dimension is at most 256 elements
-            while (s->gram_T > 32 && (size_t)s->gram_NS * J * s->gram_T * sizeof(double) > budget) s->gram_T >>= 1;
+            s->gram_T = 256; // a TMA box dimension is at most 256 elements
+            while (s->gram_T > 32 && (size_t)s->gram_NS * accept_gram_stage_doubles(J, s->gram_T) * sizeof(double) > budget) s->gram_T >>= 1;
+            s->ag_smem = (size_t)s->gram_NS * accept_gram_stage_doubles(J, s->gram_T) * sizeof(double);
         } else {
             // cp.async pipeline.  Large tiles matter (per-tile barrier/issue overhead): split the basis
             // into G column groups of <= ~40 columns (+3 row vectors when G > 1), take the largest T
@@ -677,7 +921,7 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
             if (es) s->gram_NS = atoi(es);
         }
         s->gram_smem = (size_t)s->gram_NS * Jt * s->gram_T * sizeof(double);
-        // TMA variant: 16 consumer warps = NG column groups x NE element groups.  Each element group
+        // TMA variants: 16 consumer warps = NG column groups x NE element groups.  Each element group
         // should span >= 32 double2 items (all lanes busy) and no warp may own more than kMaxCW columns.
         int NE = s->gram_T / 2 / 32;
         if (NE < 1) NE = 1;
@@ -691,10 +935,14 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
         if (s->gram_tma) gx = s->sms; // warp-specialised: one CTA per SM
         if (gx < 1) gx = 1;
         s->grid_gram = params->grid_ctas > 0 ? params->grid_ctas : (int)(tiles < gx ? (tiles < 1 ? 1 : tiles) : gx);
+        s->grid_ag = s->grid_gram;
+        if (s->fused) {
+            if ((J + s->gram_NG - 1) / s->gram_NG <= 7) s->ag_kernel = accept_gram_kernel_for<7>(objective);
+            else s->ag_kernel = accept_gram_kernel_for<kMaxCW>(objective);
+            s->ct_kernel = combine_trial_kernel_for(objective);
+        }
     }
 
-    const size_t nvecs = 4 + 2 * (size_t)s->nslots;
-    const size_t arena_bytes = nvecs * s->stride * sizeof(double);
 #define CREATE_TRY(expr)                                                                      \
     do {                                                                                      \
         cudaError_t e2_ = (expr);                                                             \
@@ -704,37 +952,30 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
             return LBFGSB200_ERR_CUDA;                                                        \
         }                                                                                     \
     } while (0)
+#define CREATE_RC(expr)                                                                       \
+    do {                                                                                      \
+        int rc2_ = (expr);                                                                    \
+        if (rc2_ < 0) {                                                                       \
+            lbfgsb200_destroy(s);                                                             \
+            return rc2_;                                                                      \
+        }                                                                                     \
+    } while (0)
     CREATE_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    CREATE_TRY(cudaEventCreate(&s->ev0));
-    CREATE_TRY(cudaEventCreate(&s->ev1));
-    // The arena ((2m+6) vectors, tens of GB) comes from the device's stream-ordered memory pool with the
-    // release threshold raised, so that destroying a solver and creating the next one of similar size
-    // re-uses the mapping instead of paying cudaMalloc/cudaFree of tens of GB (5-130 ms each way) again.
-    // lbfgsb200_trim_memory() hands the cached memory back to the driver.
-    cudaMemPool_t pool;
+    CREATE_TRY(cudaStreamCreateWithFlags(&s->capture_stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreateWithFlags(&s->ev0, cudaEventDefault));
+    CREATE_TRY(cudaEventCreateWithFlags(&s->ev1, cudaEventDefault));
+    // The arena ((2m+6) vectors, tens of GB) and the small buffers come from the library's PRIVATE stream-ordered
+    // pool (pool_alloc above): a destroyed solver's memory is re-used by the next create without a driver round trip.
+    const size_t nvecs = 4 + 2 * (size_t)s->nslots;
+    const size_t arena_bytes = nvecs * s->stride * sizeof(double);
     {
-        int dev = 0;
-        CREATE_TRY(cudaGetDevice(&dev));
-        CREATE_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
-        uint64_t keep = UINT64_MAX;
-        CREATE_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    }
-    cudaError_t e = cudaMallocAsync(&s->arena, arena_bytes, s->stream);
-    if (e == cudaErrorMemoryAllocation) {
-        // an arena cached from a destroyed solver of another size may be what is in the way: give the
-        // cache back to the driver and try once more
-        cudaGetLastError();
-        s->arena = nullptr;
-        cudaStreamSynchronize(s->stream);
-        cudaMemPoolTrimTo(pool, 0);
-        e = cudaMallocAsync(&s->arena, arena_bytes, s->stream);
-    }
-    if (e != cudaSuccess) {
-        set_error("allocation of %.2f GB for %zu vectors failed: %s", arena_bytes / 1e9, nvecs, cudaGetErrorString(e));
-        cudaGetLastError();
-        s->arena = nullptr;
-        lbfgsb200_destroy(s);
-        return LBFGSB200_ERR_NOMEM;
+        int rc_a = pool_alloc((void **)&s->arena, arena_bytes, s->stream);
+        if (rc_a < 0) {
+            const std::string why = lbfgsb200_last_error();
+            set_error("allocation of %.2f GB for %zu vectors failed (%s)", arena_bytes / 1e9, nvecs, why.c_str());
+            lbfgsb200_destroy(s);
+            return LBFGSB200_ERR_NOMEM;
+        }
     }
     // Zero only what must be zero: the work vector w (d = 0 for the x0 evaluation) and the <= 31
     // pad doubles at the end of every row (the compact kernels read rows up to the padded length).
@@ -742,55 +983,74 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     // HBM pass over (2m+6) vectors on every create().
     {
         const size_t pad = s->stride - s->n_local;
-        for (size_t v = 0; v < nvecs; ++v) {
-            if (v == 3) CREATE_TRY(cudaMemsetAsync(s->arena + v * s->stride, 0, s->stride * sizeof(double), s->stream));
-            else if (pad) CREATE_TRY(cudaMemsetAsync(s->arena + v * s->stride + s->n_local, 0, pad * sizeof(double), s->stream));
-        }
+        CREATE_TRY(cudaMemsetAsync(s->arena + 3 * s->stride, 0, s->stride * sizeof(double), s->stream));
+        if (pad) // one strided memset for the pad of every row
+            CREATE_TRY(cudaMemset2DAsync(s->arena + s->n_local, s->stride * sizeof(double), 0, pad * sizeof(double), nvecs, s->stream));
     }
+    // ---- ONE allocation for all small device buffers ----
     size_t npart = (size_t)kMaxQ * (size_t)s->grid;
-    if (params->direction == LBFGSB200_DIR_COMPACT) {
-        const size_t need = (size_t)3 * (2 * params->m + 1) * (size_t)s->grid_gram;
-        if (need > npart) npart = need;
-    }
-    CREATE_TRY(cudaMalloc(&s->partials, sizeof(double) * npart));
-    CREATE_TRY(cudaMemsetAsync(s->partials, 0, sizeof(double) * npart, s->stream));
     size_t gram_nb = 0, gram_cnt = 0;
-    if (params->direction == LBFGSB200_DIR_COMPACT) {
+    if (compact) {
+        const size_t need = ((size_t)3 * J + 1) * (size_t)s->grid_gram;
+        if (need > npart) npart = need;
         gram_nb = (size_t)(2 * s->nslots + 1);
-        gram_cnt = (size_t)3 * (2 * params->m + 1);
-        const size_t total = gram_nb * gram_nb + gram_cnt * (size_t)(nranks + 1) + (size_t)(2 * params->m + 1);
-        CREATE_TRY(cudaMalloc(&s->gram, sizeof(double) * total));
-        CREATE_TRY(cudaMemsetAsync(s->gram, 0, sizeof(double) * total, s->stream));
-        // opt every pass-A variant in to the device's full dynamic shared memory once (the limit is per
-        // function and process-wide; occupancy still follows the size actually passed at launch)
-        int dev = 0, optin = 0;
-        CREATE_TRY(cudaGetDevice(&dev));
-        CREATE_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        if ((size_t)optin < s->gram_smem + 4096) {
-            set_error("pass A needs %zu bytes of shared memory, the device offers %d", s->gram_smem, optin);
+        gram_cnt = (size_t)3 * J + kRowsExtra;
+        s->gram_doubles = gram_nb * gram_nb + gram_cnt * (size_t)(nranks + 1) + (size_t)J;
+    }
+    s->trace_rows = trace_rows;
+    size_t off = 0;
+    const size_t off_st = off;        off = align_up(off + sizeof(DevState), 256);
+    const size_t off_part = off;      off = align_up(off + sizeof(double) * npart, 256);
+    const size_t off_pkt = off;       off = align_up(off + sizeof(double) * kPacket * (size_t)(nranks + 1), 256);
+    const size_t off_gram = off;      off = align_up(off + sizeof(double) * s->gram_doubles, 256);
+    const size_t off_maps = off;      off = align_up(off + (compact && s->gram_tma ? sizeof(ArenaMaps) : 0), 256);
+    const size_t off_trace = off;     off = align_up(off + sizeof(double) * LBFGSB200_TRACE_COLS * trace_rows, 256);
+    int tl_cap = 0;
+    if (const char *et = getenv("LBFGSB200_TIMELINE")) tl_cap = atoi(et) > 0 ? atoi(et) : 0;
+    const size_t off_tl = off;        off = align_up(off + sizeof(unsigned long long) * 3 * (size_t)tl_cap, 256);
+    CREATE_RC(pool_alloc(&s->aux, off, s->stream));
+    char *aux = (char *)s->aux;
+    CREATE_TRY(cudaMemsetAsync(aux, 0, off_trace, s->stream)); // state, partials, packets, Gram block, maps
+    if (trace_rows) CREATE_TRY(cudaMemsetAsync(aux + off_trace, 0, off_tl - off_trace, s->stream));
+    s->d_st = (DevState *)(aux + off_st);
+    s->partials = (double *)(aux + off_part);
+    s->pkt = (double *)(aux + off_pkt);
+    if (s->gram_doubles) s->gram = (double *)(aux + off_gram);
+    if (compact && s->gram_tma) s->arena_maps = (ArenaMaps *)(aux + off_maps);
+    if (trace_rows) s->trace = (double *)(aux + off_trace);
+    if (tl_cap) s->timeline = (unsigned long long *)(aux + off_tl);
+    if (compact) {
+        // opt every pass-A variant in to the device's full dynamic shared memory (the limit is per function and
+        // per device; occupancy still follows the size actually passed at launch).  Done once per device.
+        static bool opted[kMaxDevices] = {};
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        if (!opted[s->device]) {
+            int optin = 0;
+            CREATE_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
+            CREATE_TRY(cudaFuncSetAttribute((const void *)k_scalar, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(sizeof(double) * kMaxCols * kMaxCols)));
+            const void *variants[] = {(const void *)k_gram<3>, (const void *)k_gram<6>, (const void *)k_gram<kMaxCW>,
+                                      (const void *)k_gram_tma2d<7>, (const void *)k_gram_tma2d<kMaxCW>,
+                                      (const void *)k_accept_gram<ObjQuadratic, 7>, (const void *)k_accept_gram<ObjQuadratic, kMaxCW>,
+                                      (const void *)k_accept_gram<ObjRosenbrock, 7>, (const void *)k_accept_gram<ObjRosenbrock, kMaxCW>,
+                                      (const void *)k_accept_gram<ObjTridiag, 7>, (const void *)k_accept_gram<ObjTridiag, kMaxCW>};
+            for (const void *fn : variants) {
+                cudaFuncAttributes fa;
+                CREATE_TRY(cudaFuncGetAttributes(&fa, fn));
+                CREATE_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+            }
+            s_optin[s->device] = optin;
+            opted[s->device] = true;
+        }
+        const size_t need = (s->fused ? s->ag_smem : s->gram_smem) + 4096;
+        if ((size_t)s_optin[s->device] < need) {
+            set_error("pass A needs %zu bytes of shared memory, the device offers %d", need, s_optin[s->device]);
             lbfgsb200_destroy(s);
             return LBFGSB200_ERR_INVALID;
         }
-        CREATE_TRY(cudaFuncSetAttribute((const void *)k_scalar, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(sizeof(double) * kMaxCols * kMaxCols)));
-        const void *variants[] = {(const void *)k_gram<3>, (const void *)k_gram<6>, (const void *)k_gram<kMaxCW>,
-                                  (const void *)k_gram_tma<7>, (const void *)k_gram_tma<kMaxCW>,
-                                  (const void *)k_gram_tma2d<7>, (const void *)k_gram_tma2d<kMaxCW>};
-        for (const void *fn : variants) {
-            cudaFuncAttributes fa;
-            CREATE_TRY(cudaFuncGetAttributes(&fa, fn));
-            CREATE_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
-        }
     }
-    CREATE_TRY(cudaMalloc(&s->pkt, sizeof(double) * kPacket * (size_t)(nranks + 1)));
-    CREATE_TRY(cudaMemsetAsync(s->pkt, 0, sizeof(double) * kPacket * (size_t)(nranks + 1), s->stream));
-    s->trace_rows = trace_rows;
-    if (trace_rows) {
-        CREATE_TRY(cudaMalloc(&s->trace, sizeof(double) * LBFGSB200_TRACE_COLS * trace_rows));
-        CREATE_TRY(cudaMemsetAsync(s->trace, 0, sizeof(double) * LBFGSB200_TRACE_COLS * trace_rows, s->stream));
-    }
-    CREATE_TRY(cudaMalloc(&s->d_st, sizeof(DevState)));
-    CREATE_TRY(cudaHostAlloc(&s->h_ctrl, sizeof(Ctrl), cudaHostAllocDefault));
+    s->h_ctrl = (Ctrl *)pinned_block_get();
+    if (!s->h_ctrl) { set_error("cudaHostAlloc of the control block failed"); lbfgsb200_destroy(s); return LBFGSB200_ERR_NOMEM; }
     memset(s->h_ctrl, 0, sizeof(Ctrl));
 
     DevState &st = s->h_snapshot;
@@ -809,6 +1069,7 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     st.nranks = nranks;
     st.grid = s->grid;
     st.grid_accept = s->grid_accept;
+    st.arena0 = s->arena;
     st.x = s->arena;
     st.x_alt = s->arena + s->stride;
     st.g = s->arena + 2 * s->stride;
@@ -816,6 +1077,7 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     st.S = s->arena + 4 * s->stride;
     st.Y = st.S + (size_t)s->nslots * s->stride;
     st.stride = (long long)s->stride;
+    st.fused = s->fused ? 1 : 0;
     if (comm && comm->p2p) {
         st.p2p = 1;
         const char *et = getenv("LBFGSB200_P2P_TIMEOUT_S");
@@ -845,20 +1107,13 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     st.lsp.bt_tol = params->backtracking_tol;
     st.lsp.wolfe_min = params->wolfe_min;
     st.status = LBFGSB200_RUNNING;
-    if (const char *et = getenv("LBFGSB200_TIMELINE")) {
-        st.tl_cap = atoi(et);
-        if (st.tl_cap > 0) {
-            CREATE_TRY(cudaMalloc(&s->timeline, sizeof(unsigned long long) * 3 * (size_t)st.tl_cap));
-            st.tl = s->timeline;
-        }
-    }
-    if (s->gram && s->gram_tma == 2) {
-        int rc_maps = build_gram_maps(s, st);
-        if (rc_maps < 0) { lbfgsb200_destroy(s); return rc_maps; }
-    }
+    st.tl_cap = tl_cap;
+    st.tl = s->timeline;
+    if (s->arena_maps) CREATE_RC(build_arena_maps(s, s->arena_maps));
     CREATE_TRY(cudaMemcpyAsync(s->d_st, &st, sizeof st, cudaMemcpyHostToDevice, s->stream));
-    CREATE_TRY(cudaStreamSynchronize(s->stream));
+    // no synchronisation here: everything above is ordered on the solver stream, which every later call uses
 #undef CREATE_TRY
+#undef CREATE_RC
     *out = s;
     return 0;
 }
@@ -866,26 +1121,22 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
 void lbfgsb200_destroy(lbfgsb200_solver_t *s)
 {
     if (!s) return;
+    if (s->device >= 0) cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int c = 0; c < LBFGSB200_PROFILE_CLASSES; ++c)
         for (cudaEvent_t e : s->prof_ev[c]) cudaEventDestroy(e);
-    if (s->arena && s->stream) {
-        cudaFreeAsync(s->arena, s->stream); // back to the pool (see lbfgsb200_create)
+    if (s->stream) { // back to the private pool (see pool_alloc): stream-ordered, no device-wide synchronisation
+        if (s->arena) cudaFreeAsync(s->arena, s->stream);
+        if (s->aux) cudaFreeAsync(s->aux, s->stream);
+        if (s->cb_buf) cudaFreeAsync(s->cb_buf, s->stream);
         cudaStreamSynchronize(s->stream);
     }
-    if (s->partials) cudaFree(s->partials);
-    if (s->gram) cudaFree(s->gram);
-    if (s->gram_maps) cudaFree(s->gram_maps);
-    if (s->cb_buf) cudaFree(s->cb_buf);
-    if (s->pkt) cudaFree(s->pkt);
-    if (s->trace) cudaFree(s->trace);
-    if (s->timeline) cudaFree(s->timeline);
-    if (s->d_st) cudaFree(s->d_st);
-    if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
+    if (s->h_ctrl) pinned_block_put(s->h_ctrl);
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     if (s->graph) cudaGraphDestroy(s->graph);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->capture_stream) cudaStreamDestroy(s->capture_stream);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -899,10 +1150,10 @@ int lbfgsb200_create_callback(lbfgsb200_solver_t **out, lbfgsb200_fg_device_fn f
     lbfgsb200_solver *s = *out;
     s->cb = fn;
     s->cb_user = user;
-    cudaError_t e = cudaMalloc(&s->cb_buf, sizeof(double) * (s->stride + 8));
-    if (e == cudaSuccess) e = cudaMemset(s->cb_buf, 0, sizeof(double) * (s->stride + 8));
+    rc = pool_alloc((void **)&s->cb_buf, sizeof(double) * (s->stride + 8), s->stream);
+    cudaError_t e = rc < 0 ? cudaErrorMemoryAllocation : cudaMemsetAsync(s->cb_buf, 0, sizeof(double) * (s->stride + 8), s->stream);
     if (e != cudaSuccess) {
-        set_error("create_callback: %s", cudaGetErrorString(e));
+        if (rc >= 0) set_error("create_callback: %s", cudaGetErrorString(e));
         cudaGetLastError();
         lbfgsb200_destroy(s);
         *out = nullptr;
@@ -921,13 +1172,7 @@ struct CkptHeader {
     int64_t k_host;
 };
 
-static size_t gram_doubles_of(const lbfgsb200_solver *s)
-{
-    if (!s->gram) return 0;
-    const size_t nb = (size_t)(2 * s->nslots + 1), cnt = (size_t)3 * (2 * s->params.m + 1);
-    const int nranks = s->comm ? s->comm->nranks : 1;
-    return nb * nb + cnt * (size_t)(nranks + 1) + (size_t)(2 * s->params.m + 1);
-}
+static size_t gram_doubles_of(const lbfgsb200_solver *s) { return s->gram_doubles; }
 
 static int stream_dev_to_file(FILE *f, const double *dev, size_t count, cudaStream_t st)
 {
@@ -996,10 +1241,23 @@ int lbfgsb200_checkpoint_load(lbfgsb200_solver_t *s, const char *path)
     const int rank = s->comm ? s->comm->rank : 0, nranks = s->comm ? s->comm->nranks : 1;
     if (!rc && (h.n_local != s->n_local || h.stride != s->stride || h.m != s->params.m || h.objective != s->objective ||
                 h.direction != s->params.direction || h.profile != s->params.profile || h.rank != rank || h.nranks != nranks ||
-                h.gram_doubles != gram_doubles_of(s) || h.trace_rows != s->trace_rows)) {
+                h.gram_doubles != gram_doubles_of(s) || h.trace_rows != s->trace_rows || st.fused != s->h_snapshot.fused)) {
         set_error("checkpoint_load: the checkpoint was written by a solver of a different shape");
         rc = LBFGSB200_ERR_INVALID;
     }
+    if (!rc) { // the whole payload must be there BEFORE the first byte of this solver's state is replaced
+        const long pos = ftell(f);
+        fseek(f, 0, SEEK_END);
+        const long end = ftell(f);
+        fseek(f, pos, SEEK_SET);
+        const size_t payload = sizeof(double) * ((size_t)h.nvecs * h.stride + h.gram_doubles + (size_t)s->trace_rows * LBFGSB200_TRACE_COLS);
+        if (pos < 0 || end < 0 || (size_t)(end - pos) != payload) {
+            set_error("checkpoint_load: %s is truncated (%ld payload bytes, expected %zu)", path, end - pos, payload);
+            rc = LBFGSB200_ERR_INVALID;
+        }
+    }
+    if (rc) { fclose(f); return rc; }
+    s->x0_set = false; // from here on a failure leaves the arena half-replaced: the handle needs set_x0 or a good load
     if (!rc) rc = stream_file_to_dev(f, s->arena, h.nvecs * h.stride, s->stream);
     if (!rc && h.gram_doubles) rc = stream_file_to_dev(f, s->gram, h.gram_doubles, s->stream);
     if (!rc && s->trace_rows) rc = stream_file_to_dev(f, s->trace, s->trace_rows * LBFGSB200_TRACE_COLS, s->stream);
@@ -1007,13 +1265,14 @@ int lbfgsb200_checkpoint_load(lbfgsb200_solver_t *s, const char *path)
     if (rc) return rc;
     // scalars come from the file; every pointer and handle from this solver
     const DevState &cur = s->h_snapshot;
+    st.arena0 = s->arena;
     st.x = h.x_is_alt ? s->arena + s->stride : s->arena;
     st.x_alt = h.x_is_alt ? s->arena : s->arena + s->stride;
     st.g = cur.g; st.w = cur.w; st.S = cur.S; st.Y = cur.Y;
     st.partials = cur.partials; st.send = cur.send; st.recv = cur.recv; st.trace = cur.trace;
     st.gram = cur.gram; st.gram_rows = cur.gram_rows; st.gram_recv = cur.gram_recv; st.delta = cur.delta;
     st.mail = cur.mail; st.peers = cur.peers; st.p2p = cur.p2p; st.p2p_timeout_ns = cur.p2p_timeout_ns;
-    st.cond_outer = cur.cond_outer; st.cond_inner = cur.cond_inner; st.use_graph = cur.use_graph;
+    st.cond_outer = cur.cond_outer; st.cond_inner = cur.cond_inner; st.cond_fix = cur.cond_fix; st.use_graph = cur.use_graph;
     st.tl = cur.tl; st.tl_cap = cur.tl_cap; st.tl_n = cur.tl_n;
     st.max_iterations = cur.max_iterations; st.tolerance = cur.tolerance; st.lsp = cur.lsp; // the new handle's limits apply
     if (st.status != LBFGSB200_CONVERGED && st.status != LBFGSB200_LS_FAILED && st.k < st.max_iterations) {
@@ -1021,6 +1280,7 @@ int lbfgsb200_checkpoint_load(lbfgsb200_solver_t *s, const char *path)
         st.ctrl.done = 0;
     }
     s->h_snapshot = st;
+    *s->h_ctrl = st.ctrl;
     CUDA_TRY(cudaMemcpyAsync(s->d_st, &s->h_snapshot, sizeof(DevState), cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     s->k_host = h.k_host;
@@ -1029,11 +1289,95 @@ int lbfgsb200_checkpoint_load(lbfgsb200_solver_t *s, const char *path)
     return 0;
 }
 
+// ---- host <-> device copies of whole vectors -------------------------------------------------------
+// The reference's callers hand over pageable std::vector storage.  A plain cudaMemcpy from pageable memory is staged
+// by the driver through one thread (~10 GB/s); here kCopyThreads host threads stage 4 MB chunks through pinned buffers
+// of their own, the memcpy of one chunk overlapping the DMA of the previous ones, which gets a pageable buffer close
+// to the pinned PCIe rate.  Pinned and device pointers take the direct route.
+constexpr size_t kStageChunk = (size_t)4 << 20;
+constexpr int kCopyThreads = 4, kStageBufs = 2 * kCopyThreads;
+static char *g_stage[kMaxDevices] = {}; // kStageBufs pinned chunks per device, allocated on first use, kept
+static std::mutex g_stage_mutex;        // one staged transfer per process at a time (the buffers are shared)
+
+static bool is_pageable(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+static int staged_copy(lbfgsb200_solver *s, double *dst, const double *src, size_t bytes, bool to_device)
+{
+    std::lock_guard<std::mutex> lock(g_stage_mutex);
+    const int dev = s->device;
+    if (!g_stage[dev]) CUDA_TRY(cudaHostAlloc((void **)&g_stage[dev], kStageChunk * kStageBufs, cudaHostAllocPortable));
+    const size_t nchunks = (bytes + kStageChunk - 1) / kStageChunk;
+    int rcs[kCopyThreads] = {};
+    auto worker = [&](int t) {
+        cudaSetDevice(dev);
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        bool busy[2] = {false, false};
+        size_t pending[2] = {0, 0};
+        if (cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming) != cudaSuccess) { rcs[t] = 1; return; }
+        char *buf[2] = {g_stage[dev] + (size_t)(2 * t) * kStageChunk, g_stage[dev] + (size_t)(2 * t + 1) * kStageChunk};
+        auto span = [&](size_t c) { return (c + 1) * kStageChunk <= bytes ? kStageChunk : bytes - c * kStageChunk; };
+        int slot = 0;
+        for (size_t c = t; c < nchunks && !rcs[t]; c += kCopyThreads, slot ^= 1) {
+            const size_t off = c * kStageChunk, len = span(c);
+            if (busy[slot]) { // the previous transfer through this buffer must have left it
+                if (cudaEventSynchronize(ev[slot]) != cudaSuccess) { rcs[t] = 1; break; }
+                if (!to_device) memcpy((char *)dst + pending[slot] * kStageChunk, buf[slot], span(pending[slot]));
+                busy[slot] = false;
+            }
+            if (to_device) {
+                memcpy(buf[slot], (const char *)src + off, len);
+                if (cudaMemcpyAsync((char *)dst + off, buf[slot], len, cudaMemcpyHostToDevice, s->stream) != cudaSuccess) rcs[t] = 1;
+            } else {
+                if (cudaMemcpyAsync(buf[slot], (const char *)src + off, len, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) rcs[t] = 1;
+            }
+            if (cudaEventRecord(ev[slot], s->stream) != cudaSuccess) rcs[t] = 1;
+            busy[slot] = true;
+            pending[slot] = c;
+        }
+        for (int k = 0; k < 2; ++k) {
+            if (busy[slot]) {
+                if (cudaEventSynchronize(ev[slot]) != cudaSuccess) rcs[t] = 1;
+                else if (!to_device) memcpy((char *)dst + pending[slot] * kStageChunk, buf[slot], span(pending[slot]));
+                busy[slot] = false;
+            }
+            slot ^= 1;
+        }
+        cudaEventDestroy(ev[0]);
+        cudaEventDestroy(ev[1]);
+    };
+    std::thread th[kCopyThreads];
+    const int nthreads = (int)(nchunks < (size_t)kCopyThreads ? nchunks : (size_t)kCopyThreads);
+    for (int t = 1; t < nthreads; ++t) th[t] = std::thread(worker, t);
+    worker(0);
+    for (int t = 1; t < nthreads; ++t) th[t].join();
+    for (int t = 0; t < nthreads; ++t)
+        if (rcs[t]) { set_error("staged %s copy failed: %s", to_device ? "host-to-device" : "device-to-host", cudaGetErrorString(cudaGetLastError())); return LBFGSB200_ERR_CUDA; }
+    return 0;
+}
+
+static int copy_vector(lbfgsb200_solver *s, double *dst, const double *src, size_t count, bool to_device)
+{
+    const size_t bytes = count * sizeof(double);
+    const void *host_side = to_device ? (const void *)src : (const void *)dst;
+    if (bytes >= 2 * kStageChunk && is_pageable(host_side)) return staged_copy(s, dst, src, bytes, to_device);
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s->stream));
+    return 0;
+}
+
 int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local)
 {
     if (!s || !x0_local) { set_error("set_x0: NULL argument"); return LBFGSB200_ERR_INVALID; }
     // restore the pristine state (ring empty, pointers un-swapped), then evaluate f(x0), g(x0)
-    DevState st = s->h_snapshot;
+    DevState &st = s->h_snapshot;
     st.x = s->arena;
     st.x_alt = s->arena + s->stride;
     st.base = 0;
@@ -1043,16 +1387,21 @@ int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local)
     st.ctrl.done = 0;
     st.ctrl.h = 0;
     st.ctrl.k = 0;
+    st.ctrl.need_fix = 0;
+    st.steepest = 0;
+    st.pend_steepest = 0;
     st.status = LBFGSB200_RUNNING;
     st.use_graph = 0; // re-armed per run by do_iterate
     memset(&st.ls, 0, sizeof st.ls); // FLAVOR_PAR_INLINED carries state from one search to the next
     st.tl_n = 0;
     st.xL = st.xR = st.dL = st.dR = st.gL = st.gR = 0.0;
     CUDA_TRY(cudaMemcpyAsync(s->d_st, &st, sizeof st, cudaMemcpyHostToDevice, s->stream));
-    CUDA_TRY(cudaStreamSynchronize(s->stream)); // st is a stack object
-    CUDA_TRY(cudaMemcpyAsync(st.x, x0_local, s->n_local * sizeof(double), cudaMemcpyDefault, s->stream));
+    LB_TRY(copy_vector(s, st.x, x0_local, s->n_local, true));
     CUDA_TRY(cudaMemsetAsync(st.w, 0, s->stride * sizeof(double), s->stream)); // d = 0
-    if (s->comm && s->comm->nranks > 1) {
+    // record the graph while the upload is in flight (recording executes nothing; it has its own stream)
+    s->profiling = false;
+    if (wants_graph(s) && !s->graph_exec) LB_TRY(build_graph(s));
+    if (is_multi(s)) {
         // neighbours' boundary x before the first evaluation (one-element halo)
         if (s->comm->p2p) {
             k_scalar<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, -1, 0, 2, PACK_X0, 0);
@@ -1074,6 +1423,8 @@ int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local)
         s->launches += 1;
         LB_TRY(scalar_step(s, OP_INIT, 0, PACK_ACCEPT, s->grid));
         s->x_cur = s->arena + s->stride; // OP_INIT swapped x and x_alt
+    } else if (s->fused) {
+        LB_TRY(fused_accept_segment(s, 1));
     } else {
         s->accept_kernel<<<s->grid_accept, kThreads, 0, s->stream>>>(s->d_st, 1);
         s->launches += 1;
@@ -1123,7 +1474,7 @@ int lbfgsb200_iterate_profiled(lbfgsb200_solver_t *s, int64_t iterations,
 int lbfgsb200_get_x(lbfgsb200_solver_t *s, double *x_local_out)
 {
     if (!s || !x_local_out) return LBFGSB200_ERR_INVALID;
-    CUDA_TRY(cudaMemcpyAsync(x_local_out, s->h_snapshot.x, s->n_local * sizeof(double), cudaMemcpyDefault, s->stream));
+    LB_TRY(copy_vector(s, x_local_out, s->h_snapshot.x, s->n_local, false));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return 0;
 }
@@ -1157,13 +1508,25 @@ int64_t lbfgsb200_get_trace(lbfgsb200_solver_t *s, double *rows, size_t max_rows
     return (int64_t)have;
 }
 
-int lbfgsb200_solve(int objective, size_t n, const double *x0_host, double *x_out_host,
-                    const lbfgsb200_params_t *params, lbfgsb200_result_t *result, double *trace,
-                    size_t trace_rows)
+static void print_verbose(const lbfgsb200_result_t &r, const double *rows, int64_t got)
 {
-    if (!x0_host || !x_out_host || !params) { set_error("solve: NULL argument"); return LBFGSB200_ERR_INVALID; }
+    // the reference's per-iteration line (seq/lbfgs.cpp:77-78: printed at the top of iteration k
+    // with the current f and |grad|), reproduced from the device trace
+    const int64_t lines = r.status == LBFGSB200_MAX_ITER ? r.iterations : r.iterations + 1;
+    for (int64_t k = 0; k < lines; ++k) {
+        if (k == 0) printf("Iteration 0, f = %g, |grad| = %g\n", r.f0, r.gnorm0);
+        else if (k - 1 < got)
+            printf("Iteration %lld, f = %g, |grad| = %g\n", (long long)k, rows[(k - 1) * LBFGSB200_TRACE_COLS + 1],
+                   rows[(k - 1) * LBFGSB200_TRACE_COLS + 2]);
+    }
+}
+
+static int solve_single(int objective, size_t n, const double *x0_host, double *x_out_host,
+                        const lbfgsb200_params_t *params, lbfgsb200_result_t *result, double *trace, size_t trace_rows)
+{
     lbfgsb200_solver *s = nullptr;
-    int rc = lbfgsb200_create(&s, objective, n, params, nullptr, trace ? trace_rows : 0);
+    const size_t rows_wanted = trace ? trace_rows : (params->verbose ? (size_t)(params->max_iterations < 100000 ? params->max_iterations : 100000) : 0);
+    int rc = lbfgsb200_create(&s, objective, n, params, nullptr, rows_wanted);
     if (rc < 0) return rc;
     rc = lbfgsb200_set_x0(s, x0_host);
     if (rc >= 0) rc = lbfgsb200_iterate(s, (int64_t)params->max_iterations + 1);
@@ -1174,22 +1537,133 @@ int lbfgsb200_solve(int objective, size_t n, const double *x0_host, double *x_ou
     if (rc >= 0 && result) lbfgsb200_get_result(s, result);
     if (rc >= 0 && trace) lbfgsb200_get_trace(s, trace, trace_rows);
     if (rc >= 0 && params->verbose) {
-        // the reference's per-iteration line (seq/lbfgs.cpp:77-78: printed at the top of iteration k
-        // with the current f and |grad|), reproduced from the device trace
         lbfgsb200_result_t r;
         lbfgsb200_get_result(s, &r);
-        std::vector<double> rows((size_t)LBFGSB200_TRACE_COLS * (trace_rows ? trace_rows : 1));
-        const int64_t got = trace ? lbfgsb200_get_trace(s, rows.data(), trace_rows) : 0;
-        const int64_t lines = r.status == LBFGSB200_MAX_ITER ? r.iterations : r.iterations + 1;
-        for (int64_t k = 0; k < lines; ++k) {
-            if (k == 0) printf("Iteration 0, f = %g, |grad| = %g\n", r.f0, r.gnorm0);
-            else if (k - 1 < got)
-                printf("Iteration %lld, f = %g, |grad| = %g\n", (long long)k, rows[(k - 1) * LBFGSB200_TRACE_COLS + 1],
-                       rows[(k - 1) * LBFGSB200_TRACE_COLS + 2]);
-        }
+        std::vector<double> rows((size_t)LBFGSB200_TRACE_COLS * (rows_wanted ? rows_wanted : 1));
+        const int64_t got = rows_wanted ? lbfgsb200_get_trace(s, rows.data(), rows_wanted) : 0;
+        print_verbose(r, rows.data(), got);
     }
     lbfgsb200_destroy(s);
     return rc;
+}
+
+// ---- one process, several GPUs ------------------------------------------------------------------
+// The reference is ONE function called from ONE host thread (seq/benchmark.cpp:94, par/L-BFGS-Wolfe.cu:473).  Behind
+// that call the library drives P devices itself: one worker thread per GPU, each owning a contiguous shard and
+// running the ordinary per-rank solver; the ranks meet in the NVLink mailboxes (peer access enabled in-process, no
+// NCCL, no IPC).  The caller's x0 is scattered straight from its buffer (every GPU pulls its shard over its own
+// PCIe link, concurrently) and x is gathered the same way.
+int lbfgsb200_resolve_num_gpus(int requested, size_t n)
+{
+    const int visible = lbfgsb200_device_count();
+    if (visible < 1) return 0;
+    if (const char *e = getenv("LBFGSB200_NUM_GPUS")) {
+        if (requested == 0 && atoi(e) > 0) requested = atoi(e);
+    }
+    if (requested > 0) return requested;
+    // automatic: a GPU is worth adding while its shard keeps >= 2^23 elements (64 MB per vector); below that the
+    // iteration is bound by the per-step exchange latency, not by bandwidth
+    size_t want = n >> 23;
+    if (want < 1) want = 1;
+    int p = (int)(want < (size_t)visible ? want : (size_t)visible);
+    if (p > kMaxRanks) p = kMaxRanks;
+    return p;
+}
+
+static int solve_group(int P, int objective, size_t n, const double *x0_host, double *x_out_host,
+                       const lbfgsb200_params_t *params, lbfgsb200_result_t *result, double *trace, size_t trace_rows)
+{
+    if (P > lbfgsb200_device_count()) { set_error("num_gpus=%d but only %d CUDA devices are visible", P, lbfgsb200_device_count()); return LBFGSB200_ERR_INVALID; }
+    if (n / (size_t)P < 2) { set_error("n=%zu is too small for %d GPUs", n, P); return LBFGSB200_ERR_INVALID; }
+    int caller_dev = 0;
+    cudaGetDevice(&caller_dev);
+    std::vector<int> devices(P);
+    for (int r = 0; r < P; ++r) devices[r] = r;
+    std::vector<lbfgsb200_comm_t *> comms(P, nullptr);
+    int rc = lbfgsb200_comm_create_local(comms.data(), devices.data(), P);
+    if (rc < 0) { cudaSetDevice(caller_dev); return rc; }
+    lbfgsb200_params_t prm = *params;
+    prm.use_graph = 1; // the ranks advance in lock step on the device; the host threads only launch and wait
+    const size_t rows_wanted = trace ? trace_rows : (params->verbose ? (size_t)(params->max_iterations < 100000 ? params->max_iterations : 100000) : 0);
+    std::vector<lbfgsb200_solver *> solvers(P, nullptr);
+    std::vector<int> rcs(P, 0);
+    std::vector<std::string> errs(P);
+    auto on_all = [&](auto &&fn) {
+        std::vector<std::thread> th;
+        for (int r = 0; r < P; ++r)
+            th.emplace_back([&, r]() {
+                cudaSetDevice(devices[r]);
+                rcs[r] = fn(r);
+                if (rcs[r] < 0) errs[r] = lbfgsb200_last_error();
+            });
+        for (auto &t : th) t.join();
+        for (int r = 0; r < P; ++r)
+            if (rcs[r] < 0) { set_error("GPU %d: %s", devices[r], errs[r].c_str()); return rcs[r]; }
+        return 0;
+    };
+    // phase 1 (no exchange yet): every rank must have its solver before any rank waits for a peer
+    rc = on_all([&](int r) { return lbfgsb200_create(&solvers[r], objective, n, &prm, comms[r], r == 0 ? rows_wanted : 0); });
+    int status = rc;
+    if (rc >= 0) {
+        rc = on_all([&](int r) {
+            lbfgsb200_solver *s = solvers[r];
+            int e = lbfgsb200_set_x0(s, x0_host + s->offset);
+            if (e < 0) return e;
+            e = lbfgsb200_iterate(s, (int64_t)prm.max_iterations + 1);
+            if (e < 0) return e;
+            const int e2 = lbfgsb200_get_x(s, x_out_host + s->offset);
+            return e2 < 0 ? e2 : e;
+        });
+        status = rc < 0 ? rc : rcs[0];
+    }
+    if (rc >= 0) {
+        cudaSetDevice(devices[0]);
+        lbfgsb200_result_t r0;
+        lbfgsb200_get_result(solvers[0], &r0);
+        for (int r = 1; r < P; ++r) { // launches are per rank; report the sum, bytes likewise
+            cudaSetDevice(devices[r]);
+            lbfgsb200_result_t rr;
+            lbfgsb200_get_result(solvers[r], &rr);
+            r0.kernel_launches += rr.kernel_launches;
+            r0.bytes_moved += rr.bytes_moved;
+            if (rr.device_ms > r0.device_ms) r0.device_ms = rr.device_ms;
+        }
+        cudaSetDevice(devices[0]);
+        if (result) *result = r0;
+        if (trace) lbfgsb200_get_trace(solvers[0], trace, trace_rows);
+        if (params->verbose) {
+            std::vector<double> rows((size_t)LBFGSB200_TRACE_COLS * (rows_wanted ? rows_wanted : 1));
+            const int64_t got = rows_wanted ? lbfgsb200_get_trace(solvers[0], rows.data(), rows_wanted) : 0;
+            print_verbose(r0, rows.data(), got);
+        }
+    }
+    for (int r = 0; r < P; ++r)
+        if (solvers[r]) {
+            cudaSetDevice(devices[r]);
+            lbfgsb200_destroy(solvers[r]);
+        }
+    for (int r = 0; r < P; ++r)
+        if (comms[r]) {
+            cudaSetDevice(devices[r]);
+            lbfgsb200_comm_destroy(comms[r]);
+        }
+    cudaSetDevice(caller_dev);
+    return status;
+}
+
+int lbfgsb200_solve(int objective, size_t n, const double *x0_host, double *x_out_host,
+                    const lbfgsb200_params_t *params, lbfgsb200_result_t *result, double *trace,
+                    size_t trace_rows)
+{
+    if (!x0_host || !x_out_host || !params) { set_error("solve: NULL argument"); return LBFGSB200_ERR_INVALID; }
+    LB_TRY(check_params(params));
+    if (lbfgsb200_device_count() < 1) {
+        set_error("no usable CUDA device: this library has no CPU fallback");
+        return LBFGSB200_ERR_CUDA;
+    }
+    const int P = lbfgsb200_resolve_num_gpus(params->num_gpus, n);
+    if (P > 1) return solve_group(P, objective, n, x0_host, x_out_host, params, result, trace, trace_rows);
+    return solve_single(objective, n, x0_host, x_out_host, params, result, trace, trace_rows);
 }
 
 // --------------------------------------------------------------------
@@ -1419,12 +1893,16 @@ long lbfgsb200_debug_timeline(lbfgsb200_solver_t *s, unsigned long long *rows, s
 }
 int lbfgsb200_trim_memory(void)
 {
+    // hands the blocks cached in the library's private pool of the CURRENT device back to the driver
     int dev = 0;
-    cudaMemPool_t pool;
     CUDA_TRY(cudaGetDevice(&dev));
     CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
-    CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
+    cudaMemPool_t pool = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        if (dev >= 0 && dev < kMaxDevices) pool = g_pools[dev];
+    }
+    if (pool) CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
     return 0;
 }
 int lbfgsb200_mem_info(size_t *free_bytes, size_t *total_bytes)

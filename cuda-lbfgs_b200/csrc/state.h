@@ -26,7 +26,8 @@ constexpr int kPacket = 12;          // doubles per rank in the packed per-step 
 constexpr int kMaxRanks = 16;
 constexpr int kScalarThreads = 256;   // the 1-CTA scalar kernel
 constexpr int kMailRanks = 16;        // == LBFGSB200_MAIL_RANKS (comm.h)
-constexpr int kMailWidth = 304;       // == LBFGSB200_MAIL_WIDTH: >= kPacket and >= 3*(2*50+1) Gram rows
+constexpr int kMailWidth = 320;       // == LBFGSB200_MAIL_WIDTH: >= kPacket and >= 3*(2*50+1) Gram rows + kRowsExtra
+constexpr int kRowsExtra = 8;         // fused accept exchange: f, x_first, x_last, g_first, g_last (+3 spare) after the rows
 
 // scalar-kernel opcodes
 enum Op : int {
@@ -40,6 +41,13 @@ enum Op : int {
     OP_ACCEPT,       // after the accept/update kernel
     OP_COMPACT,      // compact form: Gram update + coefficient recursion
     OP_COMPACT_DIR,  // after the compact direction kernel (g.d)
+    // ---- fused compact flow (accept_gram.cuh): 2 + (t-1) scalar kernels per iteration ----
+    OP_F_INIT,       // after k_accept_gram(init): f, g.g at x0
+    OP_F_ACCEPT,     // after k_accept_gram: accept bookkeeping, curvature gate, convergence test, Gram update,
+                     //   coefficient recursion for the NEXT direction, neighbours' d boundary values
+    OP_F_DIR,        // after k_combine_trial: g.d, descent safeguard, line-search start + its first decision
+    OP_F_FIX,        // (rare) after the stand-alone pass A: the rejected pair left rows of g against the oldest pair missing
+    OP_F_BEGIN,      // graph prologue: arm the WHILE / IF conditions from the state
 };
 
 // 16-byte block the host reads back once per trial in host-stepped mode
@@ -48,6 +56,8 @@ struct Ctrl {
     int done;
     int h;
     int k;
+    int need_fix; // fused flow: the stand-alone pass A has to run before the next direction
+    int pad;
 };
 
 struct DevState {
@@ -62,6 +72,7 @@ struct DevState {
     int rank, nranks;
     int grid;         // CTAs of the 4-per-SM streaming kernels (partial count is passed per launch)
     int grid_accept;  // CTAs of the accept kernel
+    double *arena0;            // row 0 of the arena (tensor-map row arithmetic: x is row 0 or 1)
     double *x, *x_alt, *g, *w; // w: two-loop work vector q/r, ends as the direction d;
                                // x_alt: the accept kernel writes the new iterate here, then x <-> x_alt
     double *S, *Y;     // ring buffers, nslots rows of `stride` doubles
@@ -104,6 +115,14 @@ struct DevState {
     // boundary values of the neighbours' shards, refreshed once per outer iteration
     double xL, xR, dL, dR, gL, gR;
 
+    // neighbours' boundary elements of EVERY basis vector (fused compact flow): index = basis index
+    // (S slot s -> s, Y slot s -> nslots + s, g -> 2 nslots); bL: LAST element of the left neighbour's shard,
+    // bR: FIRST element of the right neighbour's.  Kept up to date from the accept packets (s = x_new - x_old and
+    // y = g_new - g_old are formed here with the neighbour's own operands), so that every rank can form its
+    // neighbours' boundary d = -sum_j delta_j b_j with the fma chain of k_combine_trial -- bit-identical to what
+    // the neighbour computes -- BEFORE the combine pass runs; the pass can then evaluate the first trial itself.
+    double bL[2 * kMaxSlots + 1], bR[2 * kMaxSlots + 1];
+
     // ---- peer-to-peer mailbox exchange (multi-GPU; see comm.h) ----
     double *mail;    // this rank's mailbox
     double **peers;  // [nranks] mailbox pointers of all ranks (own entry == mail)
@@ -111,8 +130,12 @@ struct DevState {
     unsigned long long p2p_timeout_ns; // bounded rendezvous: trap instead of hanging the GPU
 
     // ---- CUDA-graph mode: WHILE-node condition handles set by the scalar kernel ----
-    unsigned long long cond_outer, cond_inner;
+    unsigned long long cond_outer, cond_inner, cond_fix;
     int use_graph;
+    // ---- fused compact flow ----
+    int fused;          // 1: k_accept_gram / k_combine_trial flow
+    int pend_steepest;  // the descent safeguard fired AFTER the combine pass: the next k_trial rewrites d = -g itself
+    int pad0;
     long long iters_left; // iteration budget of the current iterate() call
 
     // ---- accounting: algorithmic HBM traffic in units of one local vector (8 n bytes) ----

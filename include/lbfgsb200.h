@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LBFGSB200_VERSION 100
+#define LBFGSB200_VERSION 200
 #define LBFGSB200_MAX_M 64        /* history pairs (reference default m=10; sweep goes to 50) */
 #define LBFGSB200_TRACE_COLS 8
 #define LBFGSB200_UNIQUE_ID_BYTES 128
@@ -56,8 +56,14 @@ typedef enum { LBFGSB200_FLAVOR_SEQ = 0, LBFGSB200_FLAVOR_PAR = 1, LBFGSB200_FLA
 typedef enum { LBFGSB200_PROFILE_SEQ = 0, LBFGSB200_PROFILE_CUDA = 1 } lbfgsb200_profile_t;
 
 /* search-direction algorithm: explicit two-loop (seq/lbfgs.cpp:93-143) or the
- * compact / Gram form that reads all 2m history vectors once */
-typedef enum { LBFGSB200_DIR_TWO_LOOP = 0, LBFGSB200_DIR_COMPACT = 1 } lbfgsb200_dir_t;
+ * compact / Gram form that reads all 2m history vectors once (default; m <= 50).  For the built-in
+ * objectives the compact form runs as two fused streaming kernels per iteration: accept step + the
+ * inner products of the next direction, and direction + first line-search trial. */
+typedef enum {
+    LBFGSB200_DIR_TWO_LOOP = 0,
+    LBFGSB200_DIR_COMPACT = 1,
+    LBFGSB200_DIR_AUTO = 2 /* default: compact for m <= 50, explicit two-loop above */
+} lbfgsb200_dir_t;
 
 /* built-in device objectives: par/functions.cpp:6-49, seq/benchmark.cpp:16-56 */
 typedef enum {
@@ -107,9 +113,14 @@ typedef struct {
     double backtracking_tol; /* BACKTRACKING_TOL */
     double wolfe_min;    /* WOLFE_INTERP_MIN */
     int ls_max_trials;   /* 20 in the reference (seq/line_search.cpp:73, :143) */
-    int use_graph;       /* 1: whole iteration loop runs as one CUDA graph (device-side control flow) */
+    int use_graph;       /* 1 (default): whole iteration loop runs as one CUDA graph (device-side control flow) */
     int verbose;         /* 1: print the reference's per-iteration line (seq/lbfgs.cpp:77-78) from the trace */
     int grid_ctas;       /* 0 = auto (4 CTAs x SM count); tuning/testing knob */
+    int num_gpus;        /* lbfgsb200_solve only: 1 = one GPU; P > 1 = shard over devices 0..P-1 of this process (one
+                          * worker thread per GPU, NVLink mailboxes, needs peer access); 0 = automatic: as many visible
+                          * GPUs as keep >= 2^23 elements per shard (LBFGSB200_NUM_GPUS in the environment overrides
+                          * the automatic choice).  The reference is called as one function from one thread
+                          * (seq/benchmark.cpp:94, par/L-BFGS-Wolfe.cu:473); this keeps that call shape on 8 GPUs. */
 } lbfgsb200_params_t;
 
 typedef struct {
@@ -137,7 +148,9 @@ const char *lbfgsb200_last_error(void); /* thread-local detail string of the las
 int lbfgsb200_device_count(void);       /* 0 when no CUDA device is usable */
 
 /* defaults = the reference's constants for the given line-search tree
- * (seq/config.h or par/constants.h) and lbfgs.h defaults (m=10, max_it=1000, tol=1e-5) */
+ * (seq/config.h or par/constants.h) and lbfgs.h defaults (m=10, max_it=1000, tol=1e-5); compact direction,
+ * graph mode, automatic GPU count.  Constants with which a device-side search could not terminate (shrink
+ * outside (0,1), non-positive step0 / tolerances) are refused by create / solve with LBFGSB200_ERR_INVALID. */
 int lbfgsb200_params_default(lbfgsb200_params_t *p, int flavor);
 
 /* ------------------------------------------------------------------ */
@@ -151,6 +164,8 @@ int lbfgsb200_params_default(lbfgsb200_params_t *p, int flavor);
 int lbfgsb200_solve(int objective, size_t n, const double *x0_host, double *x_out_host,
                     const lbfgsb200_params_t *params, lbfgsb200_result_t *result,
                     double *trace, size_t trace_rows);
+/* the GPU count lbfgsb200_solve uses for params.num_gpus = requested and a problem of n elements */
+int lbfgsb200_resolve_num_gpus(int requested, size_t n);
 
 /* Resumable form.  n_global is the full problem size; with comm != NULL this rank owns the
  * contiguous shard given by lbfgsb200_shard_range(n_global, rank, nranks). */
@@ -197,6 +212,10 @@ void lbfgsb200_shard_range(size_t n_global, int rank, int nranks, size_t *offset
 int lbfgsb200_comm_unique_id(char id[LBFGSB200_UNIQUE_ID_BYTES]);
 int lbfgsb200_comm_create(lbfgsb200_comm_t **out, const char id[LBFGSB200_UNIQUE_ID_BYTES],
                           int rank, int nranks);
+/* In-process communicators for nranks devices driven by threads of ONE process (what lbfgsb200_solve builds for
+ * num_gpus > 1): out[r] belongs to devices[r].  Peer access instead of IPC, no NCCL.  Each rank's solver must then be
+ * created, fed and iterated from its own host thread with devices[r] current. */
+int lbfgsb200_comm_create_local(lbfgsb200_comm_t **out, const int *devices, int nranks);
 void lbfgsb200_comm_destroy(lbfgsb200_comm_t *c);
 
 /* ------------------------------------------------------------------ */
@@ -240,8 +259,10 @@ void *lbfgsb200_device_alloc(size_t bytes);
 void lbfgsb200_device_free(void *p);
 int lbfgsb200_memcpy(void *dst, const void *src, size_t bytes);
 int lbfgsb200_set_device(int ordinal);
-/* Solver arenas are served from the device's stream-ordered memory pool and stay cached there after
- * lbfgsb200_destroy() so that the next solver does not pay the allocation again; this releases them. */
+/* Solver memory is served from a PRIVATE stream-ordered pool per device (the device's default pool, which other
+ * cudaMallocAsync users of the process share, is never touched) and stays cached there after lbfgsb200_destroy() so
+ * that the next solver does not pay the allocation again.  The library trims the pool and retries by itself when one
+ * of its allocations runs out of memory; this hands the cached blocks of the CURRENT device back on request. */
 int lbfgsb200_trim_memory(void);
 /* Diagnostic: with LBFGSB200_TIMELINE=<rows> in the environment at create time every scalar kernel records
  * (op, %globaltimer ns at entry, at exit); this copies up to cap_rows rows of 3 u64 out and returns the count.

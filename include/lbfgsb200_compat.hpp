@@ -40,8 +40,9 @@ struct CompatOptions {
     int flavor = -1;          // -1: LBFGS -> SEQ tree, LBFGS_CUDA(method) -> PAR tree, LBFGS_CUDA() -> inlined searches
     int profile = -1;         // -1: LBFGS -> SEQ outer loop, LBFGS_CUDA -> CUDA outer loop
     int objective = -1;       // -1: recognise the callbacks by probing; else LBFGSB200_OBJ_* (no probing)
-    int direction = LBFGSB200_DIR_TWO_LOOP;
-    int use_graph = 0;
+    int direction = LBFGSB200_DIR_AUTO; // compact (fused) for m <= 50, explicit two-loop above
+    int use_graph = 1;                  // the whole solve as one CUDA graph
+    int num_gpus = 0;                   // 0: as many visible GPUs as the problem size warrants (lbfgsb200.h), 1: one GPU
     const char *cuda_default_line_search = "wolfe"; // for the LBFGS_CUDA overload without a method
     lbfgsb200_result_t last_result;                 // filled by every call (the reference only prints)
 };
@@ -191,6 +192,7 @@ inline std::vector<double> run(const std::function<double(std::vector<double>)> 
     p.profile = o.profile >= 0 ? o.profile : (cuda_entry ? LBFGSB200_PROFILE_CUDA : LBFGSB200_PROFILE_SEQ);
     p.direction = o.direction;
     p.use_graph = o.use_graph;
+    p.num_gpus = o.num_gpus;
     p.line_search = ls;
     p.max_iterations = max_iterations;
     p.m = m;

@@ -37,7 +37,7 @@ def build(ref=True):
     """Compile the restatement and, where /root/reference exists, the reference itself."""
     subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
     if ref and os.path.isdir(REFERENCE_ROOT):
-        subprocess.check_call(["make", "-s", "-C", HERE, "ref", "refmain", "cudaref"])
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref", "refmain", "cudaref", "cudamain"])
 
 
 class _Params(C.Structure):
@@ -237,6 +237,17 @@ class CudaRef:
     @staticmethod
     def available(variant):
         return os.path.exists(os.path.join(HERE, "_ref", "libref_cuda_%s.so" % variant))
+
+    def own_main(self):
+        """Run the .cu file's own main() (the program the reference ships) and return its stdout."""
+        cap = 1 << 26
+        log = C.create_string_buffer(cap)
+        self.L.ref_cuda_own_main.restype = C.c_int
+        self.L.ref_cuda_own_main.argtypes = [C.c_char_p, C.c_size_t]
+        rc = self.L.ref_cuda_own_main(log, cap)
+        if rc != 0:
+            raise RuntimeError("the reference's main() returned %d" % rc)
+        return log.value.decode(errors="replace")
 
     def lbfgs(self, objective, x0, line_search="wolfe", m=10, max_iterations=1000, tolerance=1e-5):
         """Returns (x, info); info["log"] is the reference's stdout, info["alphas"] / ["gnorms"] are parsed

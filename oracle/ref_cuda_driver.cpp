@@ -42,6 +42,8 @@ vector<double> quadratic_grad(const vector<double> &X);
 double rosenbrock(const vector<double> &X);
 vector<double> rosenbrock_grad(const vector<double> &X);
 
+int reference_own_main(); // the .cu file's main(), renamed at compile time
+
 extern "C" {
 
 // Runs the reference's CUDA solver as-is.  objective: 0 quadratic, 1 rosenbrock.  line_search is used by
@@ -80,6 +82,29 @@ int ref_cuda_lbfgs(int objective, const char *line_search, size_t n, const doubl
         log[c] = 0;
     }
     return 0;
+}
+
+// The reference program itself: the file's own main() (renamed by -Dmain=reference_own_main; par/L-BFGS-Wolfe.cu:456-484
+// and its siblings: x0 ~ U(-2,2) from mt19937(42), n = 50 000, LBFGS_CUDA(rosenbrock, ..., 50000, 10, 1e-1), prints x0,
+// the progress lines, the solution and "Optimum value").  stdout is captured into log.  Returns main()'s value.
+int ref_cuda_own_main(char *log, size_t log_cap)
+{
+    ostringstream captured;
+    streambuf *old = cout.rdbuf(captured.rdbuf());
+    int rc = -1;
+    try {
+        rc = reference_own_main();
+    } catch (...) {
+        rc = -2;
+    }
+    cout.rdbuf(old);
+    if (log && log_cap) {
+        const string s = captured.str();
+        const size_t c = s.size() < log_cap - 1 ? s.size() : log_cap - 1;
+        memcpy(log, s.data(), c);
+        log[c] = 0;
+    }
+    return rc;
 }
 
 int ref_cuda_has_line_search_argument(void)

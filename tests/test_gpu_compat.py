@@ -25,6 +25,70 @@ def test_unmodified_reference_main_runs_on_the_drop_in(gpu):
     assert m and abs(float(m.group(1))) < 1e-15, r.stdout
 
 
+def _cuda_log(text):
+    """(alphas, norm_g per iteration, converged-at or None, final "Optimum value") of a CUDA-tree program's stdout."""
+    alphas, gnorms, conv, final = [], [], None, None
+    for line in text.splitlines():
+        if line.startswith("alpha: "):
+            alphas.append(float(line.split()[1]))
+        elif line.startswith("Iteration ") and "norm_g" in line:
+            gnorms.append(float(line.rsplit("=", 1)[1]))
+        elif line.startswith("Convergence achieved at iteration"):
+            conv = int(line.split()[-1])
+        elif line.startswith("Optimum value: "):
+            final = float(line.split()[-1])
+    return alphas, gnorms, conv, final
+
+
+@pytest.mark.parametrize("variant", ["host", "wolfe"])
+def test_cuda_tree_mains_run_on_the_drop_in(gpu, variant):
+    """The main() of parallel-implementation/L-BFGS.cu (n = 5, host Wolfe search) and of L-BFGS-Wolfe.cu (n = 50 000,
+    inlined Wolfe, the file BASELINE config 2 is quoted on), cut out of their files at build time and linked against the
+    shim (oracle/Makefile, target cudamain), next to the reference program itself (the same main() inside
+    oracle/_ref/libref_cuda_<variant>.so, run on this GPU): same output structure, the first iterations print the same
+    alpha and |g| to the 6 digits of operator<<, both converge to the mains' tolerance 1e-1."""
+    from oracle import CudaRef
+    exe = os.path.join(ROOT, "oracle", "_ref", "%s_main_on_b200" % variant)
+    if not os.path.exists(exe) or not CudaRef.available(variant):
+        pytest.skip("oracle/_ref/%s_main_on_b200 not built (needs /root/reference at build time)" % variant)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    want = CudaRef(variant).own_main()
+    ga, gg, gconv, gfinal = _cuda_log(r.stdout)
+    wa, wg, wconv, wfinal = _cuda_log(want)
+    assert r.stdout.startswith("First x: ") and "Found solution: " in r.stdout
+    # the x0 the program printed is the reference's
+    assert r.stdout.split("Starting")[0] == want.split("Starting")[0]
+    assert gconv is not None and wconv is not None, (gconv, wconv)
+    head = min(15, len(wa), len(ga))
+    assert head >= 3
+    for k in range(head):
+        assert abs(ga[k] - wa[k]) <= 2e-5 * abs(wa[k]), (k, ga[k], wa[k])
+        assert abs(gg[k] - wg[k]) <= 2e-5 * abs(wg[k]), (k, gg[k], wg[k])
+    assert gg[-1] <= 1e-1 and wg[-1] <= 1e-1
+    if variant == "host":  # n = 5: no summation-order freedom to speak of, the whole run is the same
+        assert gconv == wconv and len(ga) == len(wa)
+        assert abs(gfinal - wfinal) <= 1e-6 * max(abs(wfinal), 1e-12)
+    else:  # long-horizon trajectories are chaotic at rounding level (SURVEY.md App. D): same order of magnitude of work
+        assert 0.5 <= (gconv + 1) / (wconv + 1) <= 2.0, (gconv, wconv)
+    print("%s main(): converged at iteration %d (reference program: %d), final f %.6g (reference %.6g)" %
+          (variant, gconv, wconv, gfinal, wfinal))
+
+
+def test_unmodified_reference_main_on_two_gpus(gpu):
+    """LBFGSB200_NUM_GPUS=2: the same unmodified binary, the library shards the solve over two GPUs of this process."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "seq_main_on_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/seq_main_on_b200 not built (needs /root/reference at build time)")
+    if gpu.lib().lbfgsb200_device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=dict(os.environ, LBFGSB200_NUM_GPUS="2"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Converged!" in r.stdout
+    m = re.search(r"Optimum value: ([-+0-9.eE]+)", r.stdout)
+    assert m and abs(float(m.group(1))) < 1e-15, r.stdout
+
+
 @pytest.fixture(scope="module")
 def verbose_exe(tmp_path_factory, gpu):
     import subprocess as sp

@@ -198,7 +198,7 @@ def test_compact_direction_matches_oracle(gpu, oracle, golden, name):
 def test_compact_equals_two_loop_large_history(gpu):
     x0 = gpu.x0_uniform(200001, -2, 2)
     for m in (3, 33, 50):
-        a, ia, ta = gpu.solve("rosenbrock", x0, "wolfe", "par", trace_rows=60, m=m, max_iterations=60)
+        a, ia, ta = gpu.solve("rosenbrock", x0, "wolfe", "par", trace_rows=60, m=m, max_iterations=60, direction="two_loop")
         b, ib, tb = gpu.solve("rosenbrock", x0, "wolfe", "par", trace_rows=60, m=m, max_iterations=60, direction="compact")
         assert _close(tb[19][1], ta[19][1], 1e-10), (m, tb[19][1], ta[19][1])
         assert _close(ib["f"], ia["f"], 1e-6), (m, ib["f"], ia["f"])
@@ -213,7 +213,7 @@ def test_graph_mode_is_bitwise_identical_to_stepped(gpu, direction):
                                         ("tridiag", 10000, "interpolation", "par", 30), ("quadratic", 1000, "wolfe", "par", 10)):
         lo, hi = (-1000, 1000) if objective == "quadratic" else (-2, 2)
         x0 = gpu.x0_uniform(n, lo, hi)
-        a, ia, ta = gpu.solve(objective, x0, ls, flavor, trace_rows=K, max_iterations=K, direction=direction)
+        a, ia, ta = gpu.solve(objective, x0, ls, flavor, trace_rows=K, max_iterations=K, direction=direction, use_graph=0)
         b, ib, tb = gpu.solve(objective, x0, ls, flavor, trace_rows=K, max_iterations=K, direction=direction, use_graph=1)
         assert np.array_equal(a, b), (objective, direction)
         assert np.array_equal(ta, tb) and ia["status"] == ib["status"] and ia["iterations"] == ib["iterations"]
@@ -248,10 +248,11 @@ def test_graph_and_stepped_runs_can_alternate_on_one_handle(gpu):
     assert ra["iterations"] == 40 and np.array_equal(xa, xb)
 
 
-@pytest.mark.parametrize("direction", ["two_loop", "compact"])
-def test_tiny_and_ragged_sizes_match_oracle(gpu, oracle, direction):
-    """n = 1, 2, 3 and sizes around the warp / tile boundaries, odd and even, every objective."""
-    for n in (1, 2, 3, 5, 31, 64, 255, 257, 2049):
+@pytest.mark.parametrize("direction,graph", [("two_loop", 1), ("compact", 1), ("compact", 0)])
+def test_tiny_and_ragged_sizes_match_oracle(gpu, oracle, direction, graph):
+    """n = 1, 2, 3 and sizes around the warp / tile boundaries (the fused kernels use tiles of 256 and of 1016
+    elements), odd and even, every objective."""
+    for n in (1, 2, 3, 5, 31, 64, 255, 257, 1015, 1016, 1017, 2049):
         for objective, ls, flavor in (("rosenbrock", "wolfe", "par"), ("tridiag", "backtracking", "seq"),
                                       ("quadratic", "interpolation", "par")):
             lo, hi = (-2, 2)
@@ -259,7 +260,7 @@ def test_tiny_and_ragged_sizes_match_oracle(gpu, oracle, direction):
             for m in (1, 4):
                 xo, io, to = oracle.lbfgs(objective, x0, ls, flavor, m, 12, 1e-9, trace_rows=12)
                 x, info, tr = gpu.solve(objective, x0, ls, flavor, trace_rows=12, m=m, max_iterations=12, tolerance=1e-9,
-                                        direction=direction)
+                                        direction=direction, use_graph=graph)
                 assert info["status"] == io["status"], (n, objective, m, info["status"], io["status"])
                 assert abs(info["iterations"] - io["iterations"]) <= 1, (n, objective, m)
                 if info["iterations"] == io["iterations"]:
@@ -303,7 +304,7 @@ def test_solvers_of_different_history_sizes_coexist(gpu):
     x0 = gpu.x0_uniform(40000, -2, 2)
     mk = lambda m: gpu.Solver("rosenbrock", 40000, gpu.default_params("par", line_search="wolfe", m=m, max_iterations=100,
                                                                       direction="compact"), trace_rows=0)
-    a, b, c = mk(3), mk(10), mk(40)   # TMA variant, cp.async, cp.async with column groups
+    a, b, c = mk(3), mk(10), mk(40)   # three tile widths / consumer layouts of the fused accept + pass-A kernel
     for s in (a, b, c):
         s.set_x0(x0)
     for _ in range(3):
@@ -411,6 +412,62 @@ def test_cuda_profile_matches_its_restatement(gpu, oracle, direction):
         assert np.max(np.abs(x - xo)) <= 1e-8 * max(np.max(np.abs(xo)), 1e-3), tag
 
 
+@pytest.mark.parametrize("env", [{"LBFGSB200_FUSED": "0"}, {"LBFGSB200_FUSED": "0", "LBFGSB200_GRAM_TMA": "0"},
+                                 {"LBFGSB200_GRAM_TMA": "0"}])
+def test_unfused_and_cp_async_paths_match_oracle(gpu, oracle, monkeypatch, env):
+    """The compact direction has three code paths, chosen at create time: the fused two-kernel flow (default), the
+    unfused flow k_gram_tma2d -> k_combine -> k_trial -> k_accept (what user objectives run on; LBFGSB200_FUSED=0
+    forces it for the built-ins) and the cp.async pass A (the fallback for shards of >= 2^31 elements, where tensor
+    maps cannot be used; LBFGSB200_GRAM_TMA=0, which also switches the fused flow off).  All meet the same bar."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for objective, n, ls, flavor, m, K in (("rosenbrock", 10000, "wolfe", "par", 10, 20), ("rosenbrock", 4097, "interpolation", "par", 5, 20),
+                                           ("tridiag", 10000, "backtracking", "seq", 10, 9), ("rosenbrock", 30001, "wolfe", "par", 40, 20)):
+        x0 = oracle.x0(n, -2, 2)
+        xo, io, to = oracle.lbfgs(objective, x0, ls, flavor, m, K, 1e-5, trace_rows=K)
+        for graph in (0, 1):
+            x, info, tr = gpu.solve(objective, x0, ls, flavor, trace_rows=K, m=m, max_iterations=K, direction="compact", use_graph=graph)
+            assert info["status"] == io["status"] and info["iterations"] == io["iterations"], (env, objective, graph)
+            k = info["iterations"]
+            assert np.array_equal(tr[:k, 4], to[:k, 4]) and np.array_equal(tr[:k, 5], to[:k, 5]), (env, objective, graph)
+            assert relvec(x, xo) <= TOL_ITERATE, (env, objective, graph, relvec(x, xo))
+
+
+def test_pending_steepest_and_rejected_pair_paths_of_the_fused_flow(gpu, oracle):
+    """Rare branches of the fused compact flow, driven from harsh random starts (U(-4,4), tiny n, small and large m):
+    a pair rejected by the curvature gate with a FULL ring (the stand-alone pass A re-computes the g row: OP_F_FIX),
+    a rejected pair with room in the ring (column remap), and the descent safeguard firing after the combine pass
+    (k_trial rewrites d = -g itself).  Every configuration must reproduce the oracle's statuses, trial counts,
+    history sizes and iterates, in the graph and in the host-stepped loop."""
+    rng = np.random.default_rng(77)
+    seen_reject_full = seen_reject_room = 0
+    for case in range(60):
+        n = int(rng.choice([6, 20, 50, 257]))
+        m = int(rng.choice([1, 2, 3, 30]))
+        ls, flavor = [("backtracking", "seq"), ("interpolation", "par"), ("interpolation", "seq")][case % 3]
+        x0 = rng.uniform(-4, 4, n)
+        K = 25
+        xo, io, to = oracle.lbfgs("rosenbrock", x0, ls, flavor, m, K, 1e-9, trace_rows=K)
+        hist = np.concatenate([[0], to[:, 5]])
+        grew = np.diff(hist)
+        for k in range(len(grew)):
+            if grew[k] == 0 and hist[k] == m:
+                seen_reject_full += 1
+            elif grew[k] == 0:
+                seen_reject_room += 1
+        for graph in (0, 1):
+            x, info, tr = gpu.solve("rosenbrock", x0, ls, flavor, trace_rows=K, m=m, max_iterations=K, tolerance=1e-9,
+                                    direction="compact", use_graph=graph)
+            tag = (case, n, m, ls, flavor, graph)
+            assert info["status"] == io["status"] and info["iterations"] == io["iterations"], tag
+            k = info["iterations"]
+            assert np.array_equal(tr[:k, 5], to[:k, 5]), tag + (tr[:k, 5], to[:k, 5])
+            assert np.array_equal(tr[:k, 4], to[:k, 4]), tag
+            assert np.max(np.abs(x - xo)) <= 1e-8 * max(np.max(np.abs(xo)), 1e-3), tag
+    assert seen_reject_room > 0, "no start exercised the rejected-pair path"
+    print("rejected pairs: %d with a full ring, %d with room" % (seen_reject_full, seen_reject_room))
+
+
 def test_error_paths_are_loud_and_leave_the_library_usable(gpu):
     # out of device memory: a status and a message, not a crash
     p = gpu.default_params("par", m=10)
@@ -424,6 +481,13 @@ def test_error_paths_are_loud_and_leave_the_library_usable(gpu):
     # the compact direction is limited to m <= 50
     with pytest.raises(gpu.LbfgsError, match="compact direction supports"):
         gpu.Solver("rosenbrock", 1000, gpu.default_params("par", m=60, direction="compact"))
+    # constants with which a device-side search could not terminate are refused
+    for bad in (dict(shrink=1.0), dict(shrink=0.0), dict(step0=0.0), dict(backtracking_tol=0.0), dict(tolerance=-1.0)):
+        with pytest.raises(gpu.LbfgsError, match="invalid argument"):
+            gpu.Solver("rosenbrock", 1000, gpu.default_params("par", **bad))
+    # m > 50 with the default (automatic) direction falls back to the explicit two-loop recursion
+    x, info, _ = gpu.solve("rosenbrock", gpu.x0_uniform(2000, -2, 2), "wolfe", "par", m=60, max_iterations=5)
+    assert info["iterations"] == 5
     # and the library still works afterwards
     x, info, _ = gpu.solve("quadratic", gpu.x0_uniform(1000, -1000, 1000), "backtracking", "seq", tolerance=1e-8,
                            max_iterations=100)

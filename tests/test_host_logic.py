@@ -121,7 +121,7 @@ def test_library_exports_every_declared_symbol(pkg):
     for name in declared:
         assert hasattr(L, name), "library does not export " + name
     assert sorted(pkg.EXPORTS) == declared
-    assert L.lbfgsb200_version() == 100
+    assert L.lbfgsb200_version() == 200
 
 
 def test_library_is_sm100a_native(pkg):
@@ -131,6 +131,13 @@ def test_library_is_sm100a_native(pkg):
     if r.returncode != 0:
         pytest.skip("cuobjdump not available")
     assert "sm_100a" in r.stdout
+    # Blackwell-native data movement, not a recompiled sm_80 kernel: tensor-map TMA loads (UTMALDG) with mbarrier
+    # transaction counting (SYNCS) in pass A / the fused accept kernel, 128-bit global accesses in the streams
+    sass = subprocess.run(["cuobjdump", "-sass", pkg.LIB_PATH], capture_output=True, text=True).stdout
+    assert sass.count("UTMALDG.2D") >= 10, "tensor-map TMA loads are missing from the SASS"
+    assert "SYNCS" in sass and "LDG.E.128" in sass and "STG.E.128" in sass
+    for kernel in ("k_accept_gram", "k_combine_trial", "k_gram_tma2d", "k_trial", "k_scalar"):
+        assert kernel in sass, kernel
 
 
 def test_params_defaults_are_the_reference_constants(pkg):
