@@ -1,4 +1,4 @@
-// accept_gram.cuh -- the fused compact flow: two streaming kernels per iteration (+ one per extra trial).
+// accept_gram.cuh -- the fused accept + pass-A kernel of the compact flow.
 //
 //   k_accept_gram    accept step at the alpha the line search returned (x_new, g_new, s, y, f) FUSED with pass A
 //                    of the NEXT direction (the 3 x (2h'+1) inner products of s_new, y_new, g_new with the new
@@ -8,13 +8,22 @@
 //                    instead of 3 + 4 (accept) + 2h' + 1 (pass A)  =>  3 vector streams fewer per iteration.
 //                    Replaces updateSolution + host grad + updateVectors + 2 D2D copies + ddot(g,g)
 //                    (par/L-BFGS.cu:309-347) and all 3h+3 cublasDdot calls of the next iteration (:219-267).
-//   k_combine_trial  pass B (d = -sum_j delta_j b_j, g.d) FUSED with the first line-search trial: every search
-//                    starts at alpha = INITIAL_STEP_SIZE (seq/line_search.cpp:21, :72, :138), d is in registers, so
-//                    f, grad f . d at x + step0 d cost one extra read of x instead of a 2-stream trial pass, a
-//                    launch and a scalar kernel.  Replaces 2h cublasDaxpy + scaleByRho + negateVector
-//                    (par/L-BFGS.cu:233-276) and the first updateSolution + host f/grad + ddot of the search.
 //
-// Both are HBM-bound streams; tensor cores are not used (FP64, ~1 flop/B).
+// HBM-bound stream; tensor cores are not used (FP64, ~1 flop/B).
+//
+// Three warp roles, one CTA per SM, kGramStages stages of shared memory:
+//   warp 0        producer: <= 7 tensor-map TMA loads per tile (kept S / Y rows in <= 2 runs each, x, d, g_old), ONE PER
+//                 LANE so that they issue together, into the next free stage; completion is counted in bytes on
+//                 full[stage]
+//   warps 1..4    accept: wait full[stage]; one double2 item per lane: x + alpha d, the three-point stencil by warp
+//                 shuffles (warp-edge lanes read the tile / the halo boxes), s, y, g_new, f; the x, d, g_old rows of the
+//                 stage are OVERWRITTEN IN PLACE with s, y, g_new, the four vectors are stored to HBM, ready[stage] is
+//                 raised.  They run ahead of the gram warps by up to the pipeline depth: the accept step of tile k+1
+//                 overlaps the inner products of tile k.
+//   warps 5..16   gram: wait ready[stage]; rows (s, y, g_new) x all columns of the new window, exactly the loop of
+//                 k_gram_tma2d; release the stage on empty[stage]
+// No CTA-wide barrier in the tile loop; the four accept warps meet in one named barrier per tile (between the reads of
+// their neighbours' x / d and the in-place writes).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -25,41 +34,44 @@
 
 namespace lb {
 
-constexpr int kHaloSlotDoubles = 16; // one 128-byte aligned slot per halo box (TMA destinations are 128-byte aligned)
+constexpr int kAgAcceptWarps = 4;
+constexpr int kAgGramWarps = kWsConsumerWarps - kAgAcceptWarps; // 12
+constexpr int kAgMaxCW = 9; // columns per gram warp: at most ceil((2*50+1) / 12)
+
+// Stage layout (doubles), T = tile width, hk = pairs kept from the old window (h if the ring is not full, else h-1:
+// the oldest pair is evicted by the commit this kernel anticipates; a pair the curvature gate then rejects is
+// handled by the scalar kernel: columns of s_new / y_new are ignored, and with a full ring the stand-alone pass A
+// re-computes the g row):
+//   rows 0 .. hk-1        kept S rows, window order          (TMA, <= 2 boxes)
+//   rows hk .. 2hk-1      kept Y rows                        (TMA, <= 2 boxes)
+//   rows 2hk, +1, +2      x, d, g_old tiles (TMA)  ->  s_new, y_new, g_new after the accept warps
+__host__ __device__ inline size_t accept_gram_stage_doubles(int J, int T)
+{
+    return (size_t)J * T; // J = 2m+1 >= 2hk+3 rows
+}
 
 __device__ __forceinline__ void named_barrier_sync(int id, int threads)
 {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory");
 }
 
-// Stage layout (doubles), T = tile width:
-//   rows 0 .. J-1        the NEW window in column order [S 0..h'-1 | Y 0..h'-1 | g]: kept history rows arrive by
-//                        TMA, rows h'-1 (s_new), 2h'-1 (y_new), 2h' (g_new) are written by phase 1
-//   rows J, J+1, J+2     x, d, g_old tiles (TMA)
-//   then 4 halo slots    x[i0-2..i0-1], x[i0+T..i0+T+1], d[i0-2..i0-1], d[i0+T..i0+T+1]
-// hk = pairs kept from the old window (h if the ring is not full, else h-1: the oldest pair is evicted by the
-// commit this kernel anticipates; a pair the curvature gate then rejects is handled by the scalar kernel:
-// columns of s_new / y_new are ignored, and with a full ring the stand-alone pass A re-computes the g row).
-__host__ __device__ inline size_t accept_gram_stage_doubles(int J, int T)
-{
-    return (size_t)(J + 3) * T + 4 * kHaloSlotDoubles;
-}
-
 template <class OBJ, int CW>
 __global__ void __launch_bounds__(kWsThreads, 1)
-k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ maps, int T, int NG, int init)
+k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ maps, int T, int init)
 {
     if (st->ctrl.done) return;
     extern __shared__ __align__(128) double tile[];
-    __shared__ __align__(8) unsigned long long full[kGramStages], empty[kGramStages];
-    __shared__ double fsum[kWsConsumerWarps];
+    __shared__ __align__(8) unsigned long long full[kGramStages], ready[kGramStages], empty[kGramStages];
+    __shared__ double fsum[kAgAcceptWarps];
     const int h_old = init ? 0 : st->h;
     const int ks = (h_old == st->m) ? 1 : 0; // oldest pair evicted by the anticipated commit
-    const int hk = h_old - ks, hp = hk + 1, J = 2 * hp + 1;
+    const int hk = h_old - ks, hp = hk + 1, J = 2 * hp + 1; // J columns of the new window
+    const int nrow = 2 * hk + 3;                            // rows of a stage
     if (threadIdx.x == 0) {
         for (int s = 0; s < kGramStages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kWsConsumerWarps);
+            mbar_init(&ready[s], kAgAcceptWarps);
+            mbar_init(&empty[s], kAgGramWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -67,47 +79,55 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long n = st->n;
     const long long ntiles = (n + T - 1) / T;
-    const size_t stage_doubles = accept_gram_stage_doubles(J, T);
+    const int mrow = 2 * st->m + 1;
+    const size_t stage_doubles = accept_gram_stage_doubles(mrow, T);
     const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int NE = kWsConsumerWarps / NG;
+    const int T2 = T >> 1;
+    const int NE = T2 / 32 > 0 ? T2 / 32 : 1;     // element groups of 32 items (T >= 64)
+    const int NG = kAgGramWarps / NE;             // column groups: 3, 6 or 12
     double acc[CW][3];
 #pragma unroll
     for (int c = 0; c < CW; ++c) acc[c][0] = acc[c][1] = acc[c][2] = 0.0;
     double facc = 0.0;
-    const int cw = warp - 1, cg = cw % NG, eg = cw / NG;
+    const int gw = warp - 1 - kAgAcceptWarps, cg = gw % NG, eg = gw / NG; // gram-warp coordinates (warp >= 5)
 
     if (warp == 0) {
-        if (lane == 0) {
-            const int ns = st->nslots;
-            const int a0 = (st->base + ks) % ns;          // physical slot of the first kept pair
-            const int ra = min(hk, ns - a0), rb = hk - ra; // the kept window is at most two runs of slots
-            const int row_x = (st->x == st->arena0) ? 0 : 1;
-            const unsigned bytes = (unsigned)(((size_t)(2 * hk + 3) * T + 8) * sizeof(double));
-            for (long long k = 0; k < my_tiles; ++k) {
-                const int stage = (int)(k % kGramStages);
-                if (k >= kGramStages) mbar_wait(&empty[stage], (unsigned)(((k / kGramStages) - 1) & 1));
-                const int col = (int)((blockIdx.x + k * (long long)gridDim.x) * T);
-                double *dst = tile + stage * stage_doubles;
-                double *halo = dst + (size_t)(J + 3) * T;
-                mbar_expect_tx(&full[stage], bytes);
-                if (ra) {
-                    tma_load_2d(dst, &maps->run[ra], col, kArenaRowS + a0, &full[stage]);
-                    tma_load_2d(dst + (size_t)hp * T, &maps->run[ra], col, kArenaRowS + ns + a0, &full[stage]);
-                }
-                if (rb) {
-                    tma_load_2d(dst + (size_t)ra * T, &maps->run[rb], col, kArenaRowS, &full[stage]);
-                    tma_load_2d(dst + (size_t)(hp + ra) * T, &maps->run[rb], col, kArenaRowS + ns, &full[stage]);
-                }
-                tma_load_2d(dst + (size_t)J * T, &maps->run[1], col, row_x, &full[stage]);
-                tma_load_2d(dst + (size_t)(J + 1) * T, &maps->run[1], col, kArenaRowW, &full[stage]);
-                tma_load_2d(dst + (size_t)(J + 2) * T, &maps->run[1], col, kArenaRowG, &full[stage]);
-                tma_load_2d(halo, &maps->halo, col - 2, row_x, &full[stage]);
-                tma_load_2d(halo + kHaloSlotDoubles, &maps->halo, col + T, row_x, &full[stage]);
-                tma_load_2d(halo + 2 * kHaloSlotDoubles, &maps->halo, col - 2, kArenaRowW, &full[stage]);
-                tma_load_2d(halo + 3 * kHaloSlotDoubles, &maps->halo, col + T, kArenaRowW, &full[stage]);
-            }
+        // ---------------- producer ----------------
+        // One thread issuing every box of a tile back to back is the bottleneck (a tensor-map TMA instruction costs
+        // ~200 cycles to issue): lanes 0..6 each own ONE box of the tile and issue them in the same cycle.
+        //   lane 0: S run A   1: Y run A   2: S run B   3: Y run B   4: x   5: d   6: g_old
+        const int ns = st->nslots;
+        const int a0 = (st->base + ks) % ns;          // physical slot of the first kept pair
+        const int ra = min(hk, ns - a0), rb = hk - ra; // the kept window is at most two runs of slots
+        const int row_x = (st->x == st->arena0) ? 0 : 1;
+        const CUtensorMap *map = &maps->run[1];
+        int row = 0;
+        size_t off = 0; // destination inside the stage, in doubles
+        bool valid = true;
+        switch (lane) {
+        case 0: map = &maps->run[ra]; row = kArenaRowS + a0; off = 0; valid = ra > 0; break;
+        case 1: map = &maps->run[ra]; row = kArenaRowS + ns + a0; off = (size_t)hk * T; valid = ra > 0; break;
+        case 2: map = &maps->run[rb]; row = kArenaRowS; off = (size_t)ra * T; valid = rb > 0; break;
+        case 3: map = &maps->run[rb]; row = kArenaRowS + ns; off = (size_t)(hk + ra) * T; valid = rb > 0; break;
+        case 4: row = row_x; off = (size_t)(2 * hk) * T; break;
+        case 5: row = kArenaRowW; off = (size_t)(2 * hk + 1) * T; break;
+        case 6: row = kArenaRowG; off = (size_t)(2 * hk + 2) * T; break;
+        default: valid = false; break;
         }
-    } else {
+        const unsigned bytes = (unsigned)((size_t)nrow * T * sizeof(double));
+        for (long long k = 0; k < my_tiles; ++k) {
+            const int stage = (int)(k % kGramStages);
+            if (lane == 0) {
+                if (k >= kGramStages) mbar_wait(&empty[stage], (unsigned)(((k / kGramStages) - 1) & 1));
+                mbar_expect_tx(&full[stage], bytes);
+            }
+            __syncwarp();
+            const int col = (int)((blockIdx.x + k * (long long)gridDim.x) * T);
+            if (valid) tma_load_2d(tile + stage * stage_doubles + off, map, col, row, &full[stage]);
+        }
+    } else if (warp <= kAgAcceptWarps) {
+        // ---------------- accept warps ----------------
+        const int aw = warp - 1;
         const double alpha = init ? 0.0 : st->ls.alpha;
         const double xtL = st->xL + alpha * st->dL, xtR = st->xR + alpha * st->dR;
         const long long goff = st->goff, nglob = st->nglob;
@@ -116,57 +136,125 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
         const size_t sp = (size_t)spare_slot(*st) * (size_t)st->stride;
         double *__restrict__ s_out = st->S + sp;
         double *__restrict__ y_out = st->Y + sp;
-        const int r0 = hp - 1, r1 = 2 * hp - 1, r2 = 2 * hp;
-        const int T2 = T >> 1, slice2 = T2 / NE;
-        const int t = cw * 32 + lane; // phase-1 element of this thread within the tile (consumer warps 0..T/32-1)
+        const int e = aw * 32 + lane;   // double2 item of this lane within the tile
+        const bool act = e < T2;
+        // The element just outside the tile (left of its first, right of its last element) is the only thing the
+        // stencil needs that the tile does not hold.  The one lane on each tile edge fetches it from global memory ONE
+        // TILE AHEAD into registers (x is not written by this kernel -- the new iterate goes to x_alt -- nor is d).
+        const bool edge_l = act && e == 0, edge_r = act && e == T2 - 1;
+        const double *__restrict__ gx = st->x;
+        const double *__restrict__ gd = st->w;
+        double hx = 0.0, hd = 0.0; // halo of the CURRENT tile (left for edge_l, right for edge_r)
+        auto halo_fetch = [&](long long k, double &ox, double &od) {
+            ox = od = 0.0;
+            if (k >= my_tiles || !(edge_l || edge_r)) return;
+            const long long col = (blockIdx.x + k * (long long)gridDim.x) * T;
+            const long long idx = edge_l ? col - 1 : col + T;
+            if (idx >= 0 && idx < n) {
+                ox = gx[idx];
+                od = gd[idx];
+            }
+        };
+        halo_fetch(0, hx, hd);
         for (long long k = 0; k < my_tiles; ++k) {
             const int stage = (int)(k % kGramStages);
+            double nx, nd;
+            halo_fetch(k + 1, nx, nd); // in flight while this tile is processed
             mbar_wait(&full[stage], (unsigned)((k / kGramStages) & 1));
             double *cur = tile + stage * stage_doubles;
-            // ---------------- phase 1: the accept step on this tile ----------------
-            if (t < T) {
-                const double *in_x = cur + (size_t)J * T, *in_d = in_x + T, *in_g = in_d + T;
-                const double *halo = cur + (size_t)(J + 3) * T;
-                const long long e = (blockIdx.x + k * (long long)gridDim.x) * T + t;
-                double sv = 0.0, yv = 0.0, gv = 0.0;
-                if (e < n) {
-                    const double xc = in_x[t], dc = in_d[t], go = in_g[t];
-                    const double xt = xc + alpha * dc; // add(x, scalarProduct(alpha, d)): mul, then add
-                    double l = 0.0, r = 0.0;
-                    if (OBJ::kStencil) {
-                        if (e == 0) l = xtL;
-                        else if (t > 0) l = in_x[t - 1] + alpha * in_d[t - 1];
-                        else l = halo[1] + alpha * halo[2 * kHaloSlotDoubles + 1];
-                        if (e + 1 >= n) r = xtR;
-                        else if (t + 1 < T) r = in_x[t + 1] + alpha * in_d[t + 1];
-                        else r = halo[kHaloSlotDoubles] + alpha * halo[3 * kHaloSlotDoubles];
-                    }
-                    const long long G = goff + e;
-                    double ft;
-                    OBJ::eval(l, xt, r, G > 0, G < nglob - 1, ft, gv);
-                    sv = xt - xc; // s = x_new - x   (seq/lbfgs.cpp:177)
-                    yv = gv - go; // y = g_new - g   (seq/lbfgs.cpp:178)
-                    x_new[e] = xt;
-                    g_out[e] = gv;
-                    s_out[e] = sv;
-                    y_out[e] = yv;
-                    facc += ft;
-                }
-                cur[(size_t)r0 * T + t] = sv; // elements beyond n contribute zeros to the inner products
-                cur[(size_t)r1 * T + t] = yv;
-                cur[(size_t)r2 * T + t] = gv;
+            double *in_x = cur + (size_t)(2 * hk) * T, *in_d = in_x + T, *in_g = in_d + T;
+            const long long ge = (blockIdx.x + k * (long long)gridDim.x) * T + 2 * (long long)e; // first element of the item
+            double2 xc = make_double2(0.0, 0.0), dc = xc, go = xc;
+            if (act) {
+                xc = reinterpret_cast<const double2 *>(in_x)[e];
+                dc = reinterpret_cast<const double2 *>(in_d)[e];
+                if (!init) go = reinterpret_cast<const double2 *>(in_g)[e]; // (the arena is not cleared: the x0 evaluation must not read old bits)
             }
-            named_barrier_sync(1, 32 * kWsConsumerWarps);
-            // ---------------- phase 2: pass A on the tile (as k_gram_tma2d) ----------------
-            const double2 *cur2 = reinterpret_cast<const double2 *>(cur);
-            const int e_end = (eg + 1) * slice2;
-            for (int e = eg * slice2 + lane; e < e_end; e += 32) {
-                const double2 a0 = cur2[r0 * T2 + e], a1 = cur2[r1 * T2 + e], a2 = cur2[r2 * T2 + e];
+            const double xt0 = xc.x + alpha * dc.x; // add(x, scalarProduct(alpha, d)): mul, then add
+            const double xt1 = xc.y + alpha * dc.y;
+            double l = 0.0, r = 0.0;
+            if (OBJ::kStencil) {
+                l = __shfl_up_sync(0xffffffffu, xt1, 1);
+                r = __shfl_down_sync(0xffffffffu, xt0, 1);
+                if (act) {
+                    if (lane == 0) {
+                        const int tl = 2 * e - 1; // tile coordinate of the left neighbour
+                        if (ge == 0) l = xtL;
+                        else if (tl >= 0) l = in_x[tl] + alpha * in_d[tl];
+                        else l = hx + alpha * hd; // edge_l
+                    }
+                    if (ge + 2 >= n) r = xtR;
+                    else if (lane == 31) {
+                        const int tr = 2 * e + 2;
+                        if (tr < T) r = in_x[tr] + alpha * in_d[tr];
+                        else r = hx + alpha * hd; // edge_r
+                    }
+                }
+            }
+            // every accept warp has read what it needs of its neighbours' x / d: the rows may now be overwritten
+            named_barrier_sync(1, 32 * kAgAcceptWarps);
+            if (act) {
+                double2 a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0; // elements beyond n contribute zeros
+                if (ge < n) {
+                    const long long G0 = goff + ge;
+                    double f0, g0, f1 = 0.0, g1 = 0.0;
+                    const bool two = ge + 1 < n;
+                    if (two) {
+                        OBJ::eval(l, xt0, xt1, G0 > 0, true, f0, g0);
+                        OBJ::eval(xt0, xt1, r, true, (G0 + 1) < nglob - 1, f1, g1);
+                    } else { // odd n: the item's second element is padding
+                        OBJ::eval(l, xt0, xtR, G0 > 0, G0 < nglob - 1, f0, g0);
+                    }
+                    a0.x = xt0 - xc.x; // s = x_new - x   (seq/lbfgs.cpp:177)
+                    a1.x = g0 - go.x;  // y = g_new - g   (seq/lbfgs.cpp:178)
+                    a2.x = g0;
+                    facc += f0 + f1;
+                    const long long j2 = ge >> 1;
+                    if (two) {
+                        a0.y = xt1 - xc.y;
+                        a1.y = g1 - go.y;
+                        a2.y = g1;
+                        st2(x_new, j2, make_double2(xt0, xt1));
+                        st2(g_out, j2, a2);
+                        st2(s_out, j2, a0);
+                        st2(y_out, j2, a1);
+                    } else { // never write the zero padding of the rows
+                        x_new[ge] = xt0;
+                        g_out[ge] = a2.x;
+                        s_out[ge] = a0.x;
+                        y_out[ge] = a1.x;
+                    }
+                }
+                reinterpret_cast<double2 *>(in_x)[e] = a0; // s_new
+                reinterpret_cast<double2 *>(in_d)[e] = a1; // y_new
+                reinterpret_cast<double2 *>(in_g)[e] = a2; // g_new
+            }
+            hx = nx;
+            hd = nd;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ready[stage]); // release: the three new rows of this stage are in place
+        }
+    } else {
+        // ---------------- gram warps ----------------
+        int rowc[CW]; // shared-memory row of window column j = cg + c NG
+#pragma unroll
+        for (int c = 0; c < CW; ++c) {
+            const int j = cg + c * NG;
+            rowc[c] = (j < hk) ? j : (j == hk) ? 2 * hk : (j <= 2 * hk) ? j - 1 : j;
+        }
+        const int e = eg * 32 + lane;
+        const bool act = e < T2;
+        for (long long k = 0; k < my_tiles; ++k) {
+            const int stage = (int)(k % kGramStages);
+            mbar_wait(&ready[stage], (unsigned)((k / kGramStages) & 1));
+            const double2 *cur2 = reinterpret_cast<const double2 *>(tile + stage * stage_doubles);
+            if (act) {
+                const double2 a0 = cur2[(size_t)(2 * hk) * T2 + e], a1 = cur2[(size_t)(2 * hk + 1) * T2 + e],
+                              a2 = cur2[(size_t)(2 * hk + 2) * T2 + e];
 #pragma unroll
                 for (int c = 0; c < CW; ++c) {
-                    const int j = cg + c * NG;
-                    if (j < J) {
-                        const double2 v = cur2[j * T2 + e];
+                    if (cg + c * NG < J) { // warp-uniform
+                        const double2 v = cur2[(size_t)rowc[c] * T2 + e];
                         acc[c][0] = fma(a0.y, v.y, fma(a0.x, v.x, acc[c][0]));
                         acc[c][1] = fma(a1.y, v.y, fma(a1.x, v.x, acc[c][1]));
                         acc[c][2] = fma(a2.y, v.y, fma(a2.x, v.x, acc[c][2]));
@@ -174,12 +262,12 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (lane == 0) mbar_arrive(&empty[stage]); // this warp is done reading the stage
         }
     }
-    __syncthreads();
+    __syncthreads(); // all tiles consumed; the tile storage can be reused for the reduction
     double *red = tile; // [NE][J*3]
-    if (warp > 0) {
+    if (warp > kAgAcceptWarps) {
 #pragma unroll
         for (int c = 0; c < CW; ++c) {
             const int j = cg + c * NG;
@@ -191,8 +279,9 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
                 }
             }
         }
+    } else if (warp > 0) {
         const double fw = warp_sum(facc);
-        if (lane == 0) fsum[cw] = fw;
+        if (lane == 0) fsum[warp - 1] = fw;
     }
     __syncthreads();
     for (int q = threadIdx.x; q < J * 3; q += kWsThreads) {
@@ -202,111 +291,190 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
     }
     if (threadIdx.x == 0) { // partial of f: row 3J
         double s = 0.0;
-        for (int w = 0; w < kWsConsumerWarps; ++w) s += fsum[w];
+        for (int w = 0; w < kAgAcceptWarps; ++w) s += fsum[w];
         st->partials[(size_t)(3 * J) * gridDim.x + blockIdx.x] = s;
     }
 }
 
 // ---- pass B + first trial ------------------------------------------------------------------------
-// CTA tiles of kCtTile double2 items that OVERLAP by 2 items (4 elements) on each side: every CTA forms d for its
-// whole tile with the same fma chain (so the overlap is bit-identical in both tiles), stores only the items it
-// owns, and has the neighbours' trial values in shared memory for the three-point stencil without a second,
-// dependent pass or special edge threads.  Redundant loads: 4 of 512 items (0.8 %, L2 hits).
-constexpr int kCtItems = 2 * kThreads;       // 512 double2 items loaded per tile
-constexpr int kCtHalo = 2;                   // items of overlap on each side
-constexpr int kCtOwn = kCtItems - 2 * kCtHalo; // 508 items owned
+//   k_combine_trial  pass B (d = -sum_j delta_j b_j, g.d) FUSED with the first line-search trial: every search starts at
+//                    alpha = INITIAL_STEP_SIZE (seq/line_search.cpp:21, :72, :138) and the neighbours' boundary d is known
+//                    before this pass (DevState::bL / bR), so f and grad f . d at x + step0 d cost one extra read of x
+//                    instead of a 2-stream trial pass, a launch and a scalar kernel.  Replaces 2h cublasDaxpy +
+//                    scaleByRho + negateVector (par/L-BFGS.cu:233-276) and the first updateSolution + host f/grad + ddot
+//                    of the search (par/L-BFGS-Wolfe.cu:276-311).
+// Same producer / consumer skeleton as above: warp 0 issues <= 6 tensor-map TMA loads per tile (S and Y in <= 2 runs
+// each, g, x), one per lane; 4 consumer warps take one double2 item per lane, run the fma chain over the 2h+1 columns
+// out of shared memory (window-column order: the chain k_combine uses, so d has the same bits), store d, form the trial
+// point and evaluate the stencil by warp shuffles, warp-edge values going through a small shared-memory exchange and ONE
+// named barrier per tile.  Tiles OVERLAP by 4 elements on each side (TMA box of T columns every T-8 elements): the
+// halo of the stencil comes with the tile, recomputed with the same chain; the overlap is requested by neighbouring CTAs
+// at the same time and is served by L2.
+constexpr int kCtWarps = 4;
+constexpr int kCtThreads = 32 * (kCtWarps + 1);
+constexpr int kCtHaloItems = 2; // double2 items of overlap on each side of a tile (keeps the d stores 32-byte aligned)
+
+__host__ __device__ inline size_t combine_trial_stage_doubles(int m, int T) { return (size_t)(2 * m + 2) * T; }
 
 template <class OBJ>
-__global__ void __launch_bounds__(kThreads, kCombineCtasPerSm) k_combine_trial(const DevState *__restrict__ st)
+__global__ void __launch_bounds__(kCtThreads, 1)
+k_combine_trial(const DevState *__restrict__ st, const ArenaMaps *__restrict__ maps, int T)
 {
     if (st->ctrl.done) return;
-    __shared__ const double *cols[kMaxCols];
+    extern __shared__ __align__(128) double tile[];
+    __shared__ __align__(8) unsigned long long full[kGramStages], empty[kGramStages];
     __shared__ double coef[kMaxCols];
-    __shared__ __align__(16) double xt_s[2][2 * kCtItems];
+    __shared__ __align__(16) double2 xs[2][32 * kCtWarps]; // trial values of the tile, for the warp-edge lanes
     const int h = st->h;
     const bool steep = st->steepest || h == 0;
-    const int J = steep ? 1 : 2 * h + 1;
-    for (int j = threadIdx.x; j < J; j += kThreads) {
-        cols[j] = steep ? st->g : basis_col(st, j, h); // d = -g is the combination with the single coefficient 1
-        coef[j] = steep ? 1.0 : st->delta[j];
+    const int J = steep ? 1 : 2 * h + 1; // d = -g is the combination with the single coefficient 1 on g
+    for (int j = threadIdx.x; j < J; j += kCtThreads) coef[j] = steep ? 1.0 : st->delta[j];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGramStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kCtWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long n = st->n;
-    const long long nvec_pad = (n + 1) >> 1; // rows are zero-padded to a multiple of 32 doubles
-    const double alpha = st->lsp.step0;      // every search starts at INITIAL_STEP_SIZE
-    const double xtL = st->xL + alpha * st->dL, xtR = st->xR + alpha * st->dR;
-    const long long goff = st->goff, nglob = st->nglob;
-    const double *__restrict__ x = st->x;
-    double *__restrict__ w = st->w;
+    const long long nvec_pad = (n + 1) >> 1;
+    const int T2 = T >> 1, own2 = T2 - 2 * kCtHaloItems; // items per tile / items owned per tile
+    const long long ntiles = (nvec_pad + own2 - 1) / own2;
+    const size_t stage_doubles = combine_trial_stage_doubles(st->m, T);
+    const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     double a_gd = 0.0, a_f = 0.0, a_gdt = 0.0;
-    const long long ntiles = (nvec_pad + kCtOwn - 1) / kCtOwn;
-    int buf = 0;
-    for (long long tl = blockIdx.x; tl < ntiles; tl += gridDim.x, buf ^= 1) {
-        const long long first = tl * kCtOwn - kCtHalo; // first item loaded by this tile (may be -2)
-        const long long i0 = first + threadIdx.x, i1 = i0 + kThreads;
-        const bool ok0 = i0 >= 0 && i0 < nvec_pad, ok1 = i1 < nvec_pad;
-        double2 s0 = make_double2(0.0, 0.0), s1 = s0, g0 = s0, g1 = s0;
-#pragma unroll 8
-        for (int j = 0; j < J; ++j) {
-            const double c = coef[j];
-            const double2 v0 = ok0 ? ld2(cols[j], i0) : make_double2(0.0, 0.0);
-            const double2 v1 = ok1 ? ld2(cols[j], i1) : make_double2(0.0, 0.0);
-            s0.x = fma(c, v0.x, s0.x); s0.y = fma(c, v0.y, s0.y);
-            s1.x = fma(c, v1.x, s1.x); s1.y = fma(c, v1.y, s1.y);
-            if (j == J - 1) { g0 = v0; g1 = v1; }
+
+    if (warp == 0) {
+        // producer: lane 0: S run A   1: S run B   2: Y run A   3: Y run B   4: g   5: x   (rows in window-column order)
+        const int ns = st->nslots, b0 = st->base;
+        const int ra = steep ? 0 : min(h, ns - b0), rb = steep ? 0 : h - ra;
+        const int hh = steep ? 0 : h;
+        const int row_x = (st->x == st->arena0) ? 0 : 1;
+        const CUtensorMap *map = &maps->run[1];
+        int row = 0;
+        size_t off = 0;
+        bool valid = true;
+        switch (lane) {
+        case 0: map = &maps->run[ra]; row = kArenaRowS + b0; off = 0; valid = ra > 0; break;
+        case 1: map = &maps->run[rb]; row = kArenaRowS; off = (size_t)ra * T; valid = rb > 0; break;
+        case 2: map = &maps->run[ra]; row = kArenaRowS + ns + b0; off = (size_t)hh * T; valid = ra > 0; break;
+        case 3: map = &maps->run[rb]; row = kArenaRowS + ns; off = (size_t)(hh + ra) * T; valid = rb > 0; break;
+        case 4: row = kArenaRowG; off = (size_t)(2 * hh) * T; break;
+        case 5: row = row_x; off = (size_t)(2 * hh + 1) * T; break;
+        default: valid = false; break;
         }
-        const double2 x0 = ok0 ? ld2(x, i0) : make_double2(0.0, 0.0);
-        const double2 x1 = ok1 ? ld2(x, i1) : make_double2(0.0, 0.0);
-        s0.x = -s0.x; s0.y = -s0.y; s1.x = -s1.x; s1.y = -s1.y;
-        const bool own0 = ok0 && threadIdx.x >= kCtHalo, own1 = ok1 && threadIdx.x < kThreads - kCtHalo;
-        if (own0) {
-            st2(w, i0, s0);
-            a_gd += g0.x * s0.x + g0.y * s0.y;
+        const unsigned bytes = (unsigned)((size_t)(2 * hh + 2) * T * sizeof(double));
+        for (long long k = 0; k < my_tiles; ++k) {
+            const int stage = (int)(k % kGramStages);
+            if (lane == 0) {
+                if (k >= kGramStages) mbar_wait(&empty[stage], (unsigned)(((k / kGramStages) - 1) & 1));
+                mbar_expect_tx(&full[stage], bytes);
+            }
+            __syncwarp();
+            const long long tl = blockIdx.x + k * (long long)gridDim.x;
+            const int col = (int)(2 * (tl * own2 - kCtHaloItems)); // first element of the tile (-4 for the first tile: zero-filled)
+            if (valid) tma_load_2d(tile + stage * stage_doubles + off, map, col, row, &full[stage]);
         }
-        if (own1) {
-            st2(w, i1, s1);
-            a_gd += g1.x * s1.x + g1.y * s1.y;
-        }
-        // trial values x + alpha d of the whole tile (overlap included) for the stencil
-        double *xs = xt_s[buf];
-        reinterpret_cast<double2 *>(xs)[threadIdx.x] = make_double2(x0.x + alpha * s0.x, x0.y + alpha * s0.y);
-        reinterpret_cast<double2 *>(xs)[threadIdx.x + kThreads] = make_double2(x1.x + alpha * s1.x, x1.y + alpha * s1.y);
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const bool own = u ? own1 : own0;
-            if (!own) continue;
-            const long long i = u ? i1 : i0;
-            const int li = 2 * (threadIdx.x + u * kThreads); // local element index of the item's first element
-            const double2 dd = u ? s1 : s0;
-            const long long e = 2 * i;
-            const double c0 = xs[li], c1 = xs[li + 1];
+    } else {
+        const int cwp = warp - 1;
+        const int e = cwp * 32 + lane; // item of this lane within the tile
+        const bool in_tile = e < T2;
+        const bool owner = in_tile && e >= kCtHaloItems && e < T2 - kCtHaloItems;
+        const int hh = steep ? 0 : h;
+        const double alpha = st->lsp.step0; // every search starts at INITIAL_STEP_SIZE
+        const double xtL = st->xL + alpha * st->dL, xtR = st->xR + alpha * st->dR;
+        const long long goff = st->goff, nglob = st->nglob;
+        double *__restrict__ w = st->w;
+        for (long long k = 0; k < my_tiles; ++k) {
+            const int stage = (int)(k % kGramStages);
+            mbar_wait(&full[stage], (unsigned)((k / kGramStages) & 1));
+            const double2 *cur2 = reinterpret_cast<const double2 *>(tile + stage * stage_doubles);
+            const long long tl = blockIdx.x + k * (long long)gridDim.x;
+            const long long i = tl * own2 - kCtHaloItems + e; // global item index (may be < 0 or beyond the vector: zeros)
+            double2 s = make_double2(0.0, 0.0), gv = s, xv = s;
+            if (in_tile) {
+#pragma unroll 4
+                for (int j = 0; j < J; ++j) {
+                    const double c = coef[j];
+                    const double2 v = cur2[(size_t)j * T2 + e];
+                    s.x = fma(c, v.x, s.x);
+                    s.y = fma(c, v.y, s.y);
+                    if (j == J - 1) gv = v;
+                }
+                xv = cur2[(size_t)(2 * hh + 1) * T2 + e];
+            }
+            s.x = -s.x;
+            s.y = -s.y;
+            const bool own = owner && i < nvec_pad; // (i >= 0 for every owned item)
+            if (own) {
+                st2(w, i, s);
+                a_gd += gv.x * s.x + gv.y * s.y;
+            }
+            const double2 xt = make_double2(xv.x + alpha * s.x, xv.y + alpha * s.y);
             double l = 0.0, r = 0.0;
             if (OBJ::kStencil) {
-                l = (e == 0) ? xtL : xs[li - 1];
-                r = (e + 2 >= n) ? xtR : xs[li + 2];
+                double2 *xb = xs[k & 1];
+                xb[e < 32 * kCtWarps ? e : 0] = xt;
+                l = __shfl_up_sync(0xffffffffu, xt.y, 1);
+                r = __shfl_down_sync(0xffffffffu, xt.x, 1);
+                named_barrier_sync(2, 32 * kCtWarps);
+                if (lane == 0 && e > 0) l = xb[e - 1].y;
+                if (lane == 31 && e + 1 < T2) r = xb[e + 1].x;
             }
-            const long long G0 = goff + e;
-            double f0, q0, f1, q1;
-            OBJ::eval(l, c0, c1, G0 > 0, true, f0, q0);
-            if (e + 1 < n) {
-                OBJ::eval(c0, c1, r, true, (G0 + 1) < nglob - 1, f1, q1);
-            } else { // odd n: the item's second element is padding; element e is the last one and its right
-                     // neighbour is the next shard's first element (or does not exist)
-                OBJ::eval(l, c0, xtR, G0 > 0, G0 < nglob - 1, f0, q0);
-                f1 = 0.0;
-                q1 = 0.0;
+            if (own) {
+                const long long el = 2 * i;
+                if (el == 0) l = xtL;
+                if (el + 2 >= n) r = xtR;
+                const long long G0 = goff + el;
+                double f0, q0, f1 = 0.0, q1 = 0.0;
+                if (el + 1 < n) {
+                    OBJ::eval(l, xt.x, xt.y, G0 > 0, true, f0, q0);
+                    OBJ::eval(xt.x, xt.y, r, true, (G0 + 1) < nglob - 1, f1, q1);
+                } else { // odd n: the item's second element is padding, element el is the last of the shard
+                    OBJ::eval(l, xt.x, xtR, G0 > 0, G0 < nglob - 1, f0, q0);
+                }
+                a_f += f0 + f1;
+                a_gdt += q0 * s.x + q1 * s.y;
             }
-            a_f += f0 + f1;
-            a_gdt += q0 * dd.x + q1 * dd.y;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
         }
     }
-    double v[3] = {a_gd, a_f, a_gdt};
-    block_emit<3>(v, st->partials);
+    __syncthreads();
+    // one partial per quantity and CTA (g.d, f, grad f . d at the trial point), fixed order
+    __shared__ double red[3][kCtWarps];
+    if (warp > 0) {
+        const double v0 = warp_sum(a_gd), v1 = warp_sum(a_f), v2 = warp_sum(a_gdt);
+        if (lane == 0) { red[0][warp - 1] = v0; red[1][warp - 1] = v1; red[2][warp - 1] = v2; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double v = 0.0;
+        for (int q = 0; q < kCtWarps; ++q) v += red[threadIdx.x][q];
+        st->partials[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = v;
+    }
 }
 
-typedef void (*accept_gram_kernel_t)(const DevState *, const ArenaMaps *, int, int, int);
-typedef void (*combine_trial_kernel_t)(const DevState *);
+typedef void (*combine_trial_kernel_t)(const DevState *, const ArenaMaps *, int);
+inline combine_trial_kernel_t combine_trial_kernel_for(int objective)
+{
+    switch (objective) {
+    case LBFGSB200_OBJ_QUADRATIC: return k_combine_trial<ObjQuadratic>;
+    case LBFGSB200_OBJ_ROSENBROCK: return k_combine_trial<ObjRosenbrock>;
+    default: return k_combine_trial<ObjTridiag>;
+    }
+}
+
+typedef void (*accept_gram_kernel_t)(const DevState *, const ArenaMaps *, int, int);
+
+// columns per gram warp for history size m and tile width T (the kernel derives the same NG from T)
+inline int accept_gram_cw(int m, int T)
+{
+    const int NE = T / 64 > 0 ? T / 64 : 1, NG = kAgGramWarps / NE;
+    return (2 * m + 1 + NG - 1) / NG;
+}
 
 template <int CW>
 inline accept_gram_kernel_t accept_gram_kernel_for(int objective)
@@ -315,14 +483,6 @@ inline accept_gram_kernel_t accept_gram_kernel_for(int objective)
     case LBFGSB200_OBJ_QUADRATIC: return k_accept_gram<ObjQuadratic, CW>;
     case LBFGSB200_OBJ_ROSENBROCK: return k_accept_gram<ObjRosenbrock, CW>;
     default: return k_accept_gram<ObjTridiag, CW>;
-    }
-}
-inline combine_trial_kernel_t combine_trial_kernel_for(int objective)
-{
-    switch (objective) {
-    case LBFGSB200_OBJ_QUADRATIC: return k_combine_trial<ObjQuadratic>;
-    case LBFGSB200_OBJ_ROSENBROCK: return k_combine_trial<ObjRosenbrock>;
-    default: return k_combine_trial<ObjTridiag>;
     }
 }
 

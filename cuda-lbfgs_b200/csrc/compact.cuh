@@ -486,7 +486,7 @@ __device__ __forceinline__ void gram_rows_from_partials(const double *__restrict
     __syncthreads();
 }
 
-// pass B.  w = d = -(sum_j delta_j b_j), accumulated in window-column order; partial of g.d.
+// pass B (unfused compact flow).  w = d = -(sum_j delta_j b_j), accumulated in window-column order; partial of g.d.
 __global__ void __launch_bounds__(kThreads, kCombineCtasPerSm) k_combine(const DevState *__restrict__ st)
 {
     const int h = st->h;

@@ -378,7 +378,7 @@ __device__ void scalar_logic(DevState *st, int op, int p, const double *r)
             st->dR = -st->gR;
             ls_begin(st->lsp, st->ls, st->f, st->gd, st->f0);
             st->ctrl.ls_active = 1;
-            st->vec_streams += 1.0; // that trial also reads g and writes d (it is counted as 2 like any other)
+            st->vec_streams += 1.0; // the trial that follows also writes d (it is counted as 2 like any other)
             break;
         }
         ls_begin(st->lsp, st->ls, st->f, st->gd, st->f0);
@@ -740,10 +740,10 @@ __device__ void scalar_body(DevState *st, int op, int p, int from_comm, int pack
     const double *rv = nullptr; // gathered packets, [rank][stride]
     int rv_stride = kPacket;
     if (!from_comm) {
-        reduce_partials(st->partials, nparts, nq, r);
+        reduce_partials(st->partials, nparts, nq_of(op), r);
     } else if (from_comm == 2) {
         // peer-to-peer: pack + exchange inside this kernel
-        reduce_partials(st->partials, nparts, nq, r);
+        reduce_partials(st->partials, nparts, nq_of(op), r);
         if (threadIdx.x == 0) build_packet(st, op, pack_kind, r, pk);
         const int count = (pack_kind == PACK_NONE) ? (nq > 0 ? nq : 1) : kPacket; // sums only, or sums + boundary values
         const P2pTicket t = p2p_send(st, pk, count);

@@ -160,7 +160,7 @@ struct lbfgsb200_solver {
     bool fused = false;
     accept_gram_kernel_t ag_kernel = nullptr;
     combine_trial_kernel_t ct_kernel = nullptr;
-    size_t ag_smem = 0;
+    size_t ag_smem = 0, ct_smem = 0;
     int grid_ag = 1;
     int device = 0;
     void *aux = nullptr;        // ONE allocation for every small device buffer below (partials ... d_st)
@@ -406,7 +406,7 @@ static int run_stepped(lbfgsb200_solver *s, int64_t iterations)
 static void launch_accept_gram(lbfgsb200_solver *s, int init)
 {
     ClassTimer t(s, KC_GRAM);
-    s->ag_kernel<<<s->grid_ag, kWsThreads, s->ag_smem, s->stream>>>(s->d_st, s->arena_maps, s->gram_T, s->gram_NG, init);
+    s->ag_kernel<<<s->grid_ag, kWsThreads, s->ag_smem, s->stream>>>(s->d_st, s->arena_maps, s->gram_T, init);
     s->launches += 1;
 }
 
@@ -420,7 +420,7 @@ static int fused_direction_segment(lbfgsb200_solver *s)
 {
     {
         ClassTimer t(s, KC_COMBINE);
-        s->ct_kernel<<<s->grid_combine, kThreads, 0, s->stream>>>(s->d_st);
+        s->ct_kernel<<<s->grid_combine, kCtThreads, s->ct_smem, s->stream>>>(s->d_st, s->arena_maps, s->gram_T);
         s->launches += 1;
     }
     return scalar_step(s, OP_F_DIR, 0, PACK_NONE);
@@ -555,7 +555,7 @@ static int build_graph(lbfgsb200_solver *s)
         std::vector<cudaGraphNode_t> inner_tail;
         LB_TRY(capture_segment(s, trial_body, inner_tail, [&]() { return fused_trial_segment(s); }));
         LB_TRY(capture_segment(s, iter_body, tail, [&]() { return fused_accept_segment(s, 0); }));
-        s->graph_fixed_launches = 4; // combine + OP_F_DIR + accept_gram + OP_F_ACCEPT ; + 2 per further trial
+        s->graph_fixed_launches = 4; // combine_trial + OP_F_DIR + accept_gram + OP_F_ACCEPT ; + 2 per further trial
     } else {
         LB_TRY(add_conditional(s->graph, top_tail, h_outer, cudaGraphCondTypeWhile, &iter_body));
         s->k_host = s->params.m; // capture the passes of all m window positions; unused ones exit at once
@@ -654,8 +654,8 @@ static int do_iterate(lbfgsb200_solver *s, int64_t iterations)
     if (graph && iterations > 0) { // kernel nodes executed: fixed part per iteration + 2 per stand-alone trial
         const long long its = s->h_snapshot.k - k0, trials = s->h_snapshot.trial_evals - t0;
         if (s->fused) {
-            // prologue + per iteration {combine, OP_F_DIR, accept_gram, OP_F_ACCEPT} + 2 per trial beyond the fused first
-            // one; an iteration whose search failed ran its direction segment but no accept
+            // prologue + per iteration {combine_trial, OP_F_DIR, accept_gram, OP_F_ACCEPT} + 2 per further trial;
+            // an iteration whose search failed ran its direction segment but no accept
             const bool ls_failed_now = !was_done && s->h_snapshot.status == LBFGSB200_LS_FAILED;
             s->launches += 1 + its * s->graph_fixed_launches + 2 * (trials - its - (ls_failed_now ? 1 : 0)) + (ls_failed_now ? 2 : 0);
         } else {
@@ -903,8 +903,9 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
             const size_t budget = (size_t)(eb ? atoi(eb) : 216) * 1024;
             s->gram_NS = kGramStages;
             s->gram_T = 256; // a TMA box dimension is at most 256 elements
-            while (s->gram_T > 32 && (size_t)s->gram_NS * accept_gram_stage_doubles(J, s->gram_T) * sizeof(double) > budget) s->gram_T >>= 1;
+            while (s->gram_T > 32 && (size_t)s->gram_NS * combine_trial_stage_doubles(params->m, s->gram_T) * sizeof(double) > budget) s->gram_T >>= 1;
             s->ag_smem = (size_t)s->gram_NS * accept_gram_stage_doubles(J, s->gram_T) * sizeof(double);
+            s->ct_smem = (size_t)s->gram_NS * combine_trial_stage_doubles(params->m, s->gram_T) * sizeof(double); // one row more: x
         } else {
             // cp.async pipeline.  Large tiles matter (per-tile barrier/issue overhead): split the basis
             // into G column groups of <= ~40 columns (+3 row vectors when G > 1), take the largest T
@@ -937,9 +938,16 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
         s->grid_gram = params->grid_ctas > 0 ? params->grid_ctas : (int)(tiles < gx ? (tiles < 1 ? 1 : tiles) : gx);
         s->grid_ag = s->grid_gram;
         if (s->fused) {
-            if ((J + s->gram_NG - 1) / s->gram_NG <= 7) s->ag_kernel = accept_gram_kernel_for<7>(objective);
-            else s->ag_kernel = accept_gram_kernel_for<kMaxCW>(objective);
-            s->ct_kernel = combine_trial_kernel_for(objective);
+            const int cw = accept_gram_cw(params->m, s->gram_T);
+            if (s->gram_T < 64 || cw > kAgMaxCW) s->fused = false; // the fused kernel's warp layout needs tiles of >= 64 elements
+            else {
+                s->ag_kernel = cw <= 7 ? accept_gram_kernel_for<7>(objective) : accept_gram_kernel_for<kAgMaxCW>(objective);
+                s->ct_kernel = combine_trial_kernel_for(objective);
+                // k_combine_trial: one CTA per SM over tiles that own T/2 - 4 double2 items each
+                const long long own2 = s->gram_T / 2 - 2 * kCtHaloItems;
+                const long long ct_tiles = (((long long)s->n_local + 1) / 2 + own2 - 1) / own2;
+                s->grid_combine = params->grid_ctas > 0 ? params->grid_ctas : (int)(ct_tiles < s->sms ? ct_tiles : s->sms);
+            }
         }
     }
 
@@ -1031,9 +1039,11 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
                                             (int)(sizeof(double) * kMaxCols * kMaxCols)));
             const void *variants[] = {(const void *)k_gram<3>, (const void *)k_gram<6>, (const void *)k_gram<kMaxCW>,
                                       (const void *)k_gram_tma2d<7>, (const void *)k_gram_tma2d<kMaxCW>,
-                                      (const void *)k_accept_gram<ObjQuadratic, 7>, (const void *)k_accept_gram<ObjQuadratic, kMaxCW>,
-                                      (const void *)k_accept_gram<ObjRosenbrock, 7>, (const void *)k_accept_gram<ObjRosenbrock, kMaxCW>,
-                                      (const void *)k_accept_gram<ObjTridiag, 7>, (const void *)k_accept_gram<ObjTridiag, kMaxCW>};
+                                      (const void *)k_accept_gram<ObjQuadratic, 7>, (const void *)k_accept_gram<ObjRosenbrock, 7>,
+                                      (const void *)k_accept_gram<ObjTridiag, 7>, (const void *)k_accept_gram<ObjQuadratic, kAgMaxCW>,
+                                      (const void *)k_accept_gram<ObjRosenbrock, kAgMaxCW>, (const void *)k_accept_gram<ObjTridiag, kAgMaxCW>,
+                                      (const void *)k_combine_trial<ObjQuadratic>, (const void *)k_combine_trial<ObjRosenbrock>,
+                                      (const void *)k_combine_trial<ObjTridiag>};
             for (const void *fn : variants) {
                 cudaFuncAttributes fa;
                 CREATE_TRY(cudaFuncGetAttributes(&fa, fn));
@@ -1042,7 +1052,7 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
             s_optin[s->device] = optin;
             opted[s->device] = true;
         }
-        const size_t need = (s->fused ? s->ag_smem : s->gram_smem) + 4096;
+        const size_t need = (s->fused ? (s->ag_smem > s->ct_smem ? s->ag_smem : s->ct_smem) : s->gram_smem) + 4096;
         if ((size_t)s_optin[s->device] < need) {
             set_error("pass A needs %zu bytes of shared memory, the device offers %d", need, s_optin[s->device]);
             lbfgsb200_destroy(s);

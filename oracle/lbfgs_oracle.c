@@ -22,9 +22,25 @@
 /* vector utilities: seq/vector_utils.cpp:32-86                        */
 /* ------------------------------------------------------------------ */
 
+/* TEST-ONLY switch, used to EXPLAIN a golden file, never to define parity: with it on, every reduction
+ * (dot products, norms, the sums inside f) is accumulated in long double (64-bit mantissa) and rounded to double
+ * once, instead of the reference's naive left-to-right double sum.  Each term is still the double the reference
+ * forms.  The result is the trajectory the reference's algorithm takes when its sums carry (practically) no
+ * rounding error: the distance between the two trajectories is the reference's OWN summation noise, which at
+ * n = 1e7 reaches 1e-10 relative in the iterates after 20 steps (tests/golden/reference_large.json, "exact_sums").
+ * The product has no such mode; its deterministic tree sums are accurate to a few ulp by construction. */
+static int g_exact_sums = 0;
+void oracle_set_exact_sums(int on) { g_exact_sums = on; }
+
 /* seq/vector_utils.cpp:32-41 -- naive left-to-right sum */
 double oracle_dot(const double *a, const double *b, size_t n)
 {
+    if (g_exact_sums) {
+        long double acc = 0.0L;
+        for (size_t i = 0; i < n; ++i)
+            acc += (long double)(a[i] * b[i]);
+        return (double)acc;
+    }
     double sum = 0.;
     for (size_t i = 0; i < n; ++i)
         sum += a[i] * b[i];
@@ -34,6 +50,12 @@ double oracle_dot(const double *a, const double *b, size_t n)
 /* seq/vector_utils.cpp:78-86 */
 double oracle_norm(const double *a, size_t n)
 {
+    if (g_exact_sums) {
+        long double acc = 0.0L;
+        for (size_t i = 0; i < n; ++i)
+            acc += (long double)(a[i] * a[i]);
+        return sqrt((double)acc);
+    }
     double r = 0.;
     for (size_t i = 0; i < n; ++i)
         r += a[i] * a[i];
@@ -47,6 +69,12 @@ double oracle_norm(const double *a, size_t n)
 /* par/functions.cpp:6-14 */
 static double quadratic_f(const double *x, size_t n)
 {
+    if (g_exact_sums) {
+        long double acc = 0.0L;
+        for (size_t i = 0; i < n; ++i)
+            acc += (long double)((x[i] - 1) * (x[i] - 1));
+        return (double)acc;
+    }
     double sum = 0.0;
     for (size_t i = 0; i < n; ++i)
         sum += (x[i] - 1) * (x[i] - 1);
@@ -63,6 +91,15 @@ static void quadratic_g(const double *x, double *g, size_t n)
 /* par/functions.cpp:26-36 (same as seq/benchmark.cpp:58-68) */
 static double rosenbrock_f(const double *x, size_t n)
 {
+    if (g_exact_sums) {
+        long double acc = 0.0L;
+        for (size_t i = 0; i + 1 < n; ++i) {
+            double term1 = x[i + 1] - x[i] * x[i];
+            double term2 = 1 - x[i];
+            acc += (long double)(100.0 * term1 * term1 + term2 * term2);
+        }
+        return (double)acc;
+    }
     double sum = 0.0;
     for (size_t i = 0; i + 1 < n; ++i) {
         double term1 = x[i + 1] - x[i] * x[i];
@@ -89,6 +126,14 @@ static void rosenbrock_g(const double *x, double *g, size_t n)
 static double tridiag_f(const double *x, size_t n)
 {
     const double COEFFICIENT = 1000.0;
+    if (g_exact_sums) {
+        long double acc = 0.0L;
+        for (size_t i = 0; i < n; ++i)
+            acc += (long double)(COEFFICIENT * x[i] * x[i]);
+        for (size_t i = 0; i + 1 < n; ++i)
+            acc += (long double)((COEFFICIENT / 10.0) * x[i] * x[i + 1]);
+        return (double)acc;
+    }
     double result = 0.0;
     for (size_t i = 0; i < n; ++i)
         result += COEFFICIENT * x[i] * x[i];

@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
 
-    python oracle/make_golden_large.py [--jobs J] [--only SUBSTR] [--skip-1e8]
+    python oracle/make_golden_large.py [--jobs J] [--only SUBSTR] [--skip-1e8] [--twins-only]
 
 BASELINE config 3 (functions.cpp suite, n = 1e7, interpolation line search, m = 5/10/20) and config 2
 (Rosenbrock n = 1e8, m = 10, Wolfe).  For every case and every checkpoint K:
@@ -14,6 +14,12 @@ BASELINE config 3 (functions.cpp suite, n = 1e7, interpolation line search, m = 
     (f, ||g||, alpha, trials, history size, x[0], x[n/2]); its x at the largest K must be BIT-IDENTICAL to the
     reference's (recorded as `restatement_bitwise`; the generator aborts otherwise), which pins every trace
     row to the reference.
+
+  * "exact_sums" twin: the same restatement with every reduction accumulated in long double (oracle_set_exact_sums, a
+    TEST-ONLY switch).  It is the trajectory of the reference's algorithm WITHOUT the rounding noise of its naive
+    left-to-right sums over 1e7 .. 1e8 terms.  The distance reference <-> twin (`spread`) is the reference's own
+    summation noise; a solver with accurate (tree) sums lands on the twin, not on the reference, and is as far from
+    the reference as the twin is.  tests/test_gpu_large.py asserts exactly that.
 
 Doubles are stored as C99 hex floats.  The reference needs ~(2m+8) vectors of host memory: ~22 GB at n=1e8.
 """
@@ -58,6 +64,42 @@ def sample_index(n):
     return [(j * (n - 1)) // (NSAMPLE - 1) for j in range(NSAMPLE)]
 
 
+def run_twin(case):
+    """the exact-sums twin of a case: x samples, f, |g| at every checkpoint + the per-iteration trace"""
+    name, obj, n, (lo, hi), ls, flavor, m, tol, Ks = case
+    t_start = time.time()
+    orc = Oracle()
+    orc.set_exact_sums(True)
+    x0 = orc.x0(n, lo, hi)
+    idx = np.array(sample_index(n))
+    steps = {}
+    tr = None
+    for K in Ks:
+        x, info, tr = orc.lbfgs(obj, x0, ls, flavor, m, K, tol, trace_rows=K)
+        g = orc.grad(obj, x)
+        steps[str(K)] = dict(f=hx(orc.f(obj, x)), gnorm=hx(orc.norm(g)), status=info["status"], f_evals=info["f_evals"],
+                             g_evals=info["g_evals"], x_absmax=hx(float(np.max(np.abs(x)))), x_sample=[hx(v) for v in x[idx]])
+        del g
+    trace = [dict(k=int(r[0]), f=hx(r[1]), gnorm=hx(r[2]), alpha=hx(r[3]), trials=int(r[4]), hist=int(r[5]),
+                  x_first=hx(r[6]), x_mid=hx(r[7])) for r in tr]
+    orc.set_exact_sums(False)
+    print("%s exact-sums twin done in %.0f s" % (name, time.time() - t_start), flush=True)
+    return name, dict(steps=steps, trace=trace,
+                      what="oracle/liblbfgs_oracle.so with oracle_set_exact_sums(1): every reduction accumulated in long double")
+
+
+def add_spread(rec):
+    """distance reference <-> exact-sums twin at every checkpoint: the reference's own summation noise"""
+    unhex = float.fromhex
+    for K, tw in rec["exact_sums"]["steps"].items():
+        ref = rec["steps"][K]
+        a = np.array([unhex(v) for v in ref["x_sample"]])
+        b = np.array([unhex(v) for v in tw["x_sample"]])
+        fr, ft = unhex(ref["f"]), unhex(tw["f"])
+        tw["spread_dx"] = float(np.max(np.abs(a - b)) / unhex(ref["x_absmax"]))
+        tw["spread_df"] = abs(fr - ft) / abs(fr) if fr != 0 else abs(ft)
+
+
 def run_case(case):
     name, obj, n, (lo, hi), ls, flavor, m, tol, Ks = case
     t_start = time.time()
@@ -96,6 +138,7 @@ def main():
     ap.add_argument("--jobs", type=int, default=4)
     ap.add_argument("--only", default="")
     ap.add_argument("--skip-1e8", action="store_true")
+    ap.add_argument("--twins-only", action="store_true", help="keep the reference records of the existing file, (re)generate the exact-sums twins")
     args = ap.parse_args()
     build(ref=True)
     out = {"generator": "oracle/make_golden_large.py", "source": "oracle/_ref/libref_{seq,hybrid}.so (unmodified /root/reference "
@@ -107,6 +150,9 @@ def main():
     cases = [c for c in CASES if args.only in c[0] and not (args.skip_1e8 and c[2] > 20_000_000)]
     small = [c for c in cases if c[2] <= 20_000_000]
     big = [c for c in cases if c[2] > 20_000_000]
+    if args.twins_only:
+        small, big = [], []
+    twins = [c for c in cases if c[1] != "quadratic"]  # the separable quadratic converges in one step: no noise to explain
     if small:
         with mp.Pool(min(args.jobs, len(small))) as pool:
             for name, rec in pool.imap_unordered(run_case, small):
@@ -115,6 +161,19 @@ def main():
     for c in big:  # ~22 GB each: one at a time
         name, rec = run_case(c)
         out["cases"][name] = rec
+        json.dump(out, open(OUT, "w"), indent=0, sort_keys=True)
+    small_t = [c for c in twins if c[2] <= 20_000_000]
+    big_t = [c for c in twins if c[2] > 20_000_000]
+    if small_t:
+        with mp.Pool(min(args.jobs, len(small_t))) as pool:
+            for name, tw in pool.imap_unordered(run_twin, small_t):
+                out["cases"][name]["exact_sums"] = tw
+                add_spread(out["cases"][name])
+                json.dump(out, open(OUT, "w"), indent=0, sort_keys=True)
+    for c in big_t:
+        name, tw = run_twin(c)
+        out["cases"][name]["exact_sums"] = tw
+        add_spread(out["cases"][name])
         json.dump(out, open(OUT, "w"), indent=0, sort_keys=True)
     print("wrote", os.path.normpath(OUT))
 

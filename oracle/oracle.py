@@ -87,6 +87,12 @@ class Oracle:
         self.L.oracle_x0(seed, lo, hi, n, _p(out))
         return out
 
+    def set_exact_sums(self, on):
+        """TEST-ONLY: accumulate every reduction in long double (explains the summation noise of the reference)."""
+        self.L.oracle_set_exact_sums.restype = None
+        self.L.oracle_set_exact_sums.argtypes = [C.c_int]
+        self.L.oracle_set_exact_sums(1 if on else 0)
+
     def dot(self, a, b):
         return self.L.oracle_dot(_p(a), _p(b), a.size)
 
