@@ -58,6 +58,31 @@ def test_solver_reproduces_the_cuda_reference_goldens(gpu, cuda_golden, directio
     assert worst < 1e-11, worst
 
 
+@pytest.mark.parametrize("direction,graph", [("auto", 1), ("two_loop", 0)])
+def test_run_to_convergence_matches_the_cuda_reference(gpu, cuda_golden, direction, graph):
+    """profile=CUDA run to the tolerance (the `norm_g <= tolerance` exit, par/L-BFGS.cu:353-357) against the finals the
+    reference's own CUDA programs reached on a B200 (oracle/make_golden_cuda.py, starts near the minimiser where the
+    iteration count is stable): BASELINE.json's bar -- same verdict, iteration count within +-1, final f and |g| within
+    1e-8 relative (values that are cancellation residues of f* = 0 get the summation noise of their terms as floor)."""
+    assert cuda_golden.get("finals"), "tests/golden/cuda_reference_traces.json carries no finals: regenerate it (scripts/gpu_r2.sh cudagolden)"
+    for name, case in cuda_golden["finals"].items():
+        ls, flavor = cuda_case_setup(case)
+        n = case["n"]
+        x0 = gpu.x0_uniform(n, case["lo"], case["hi"])
+        x, info, _ = gpu.solve(case["objective"], x0, ls, flavor, profile="cuda", m=case["m"], max_iterations=case["max_iterations"],
+                               tolerance=case["tolerance"], direction=direction, use_graph=graph)
+        tag = (name, direction, info["iterations"], case["iterations"])
+        assert info["status"] == case["status"] == 0, tag
+        assert abs(info["iterations"] - case["iterations"]) <= 1, tag
+        f_ref, g_ref = unhex(case["f"]), unhex(case["gnorm"])
+        if info["iterations"] == case["iterations"]:
+            eps_f = n * 2.0 ** -52 * max(1.0, info["f0"]) * 1e-6  # f is a sum of n terms that started at f0 / n each
+            assert abs(info["f"] - f_ref) <= 1e-8 * abs(f_ref) + eps_f, tag + (info["f"], f_ref)
+            assert abs(info["gnorm"] - g_ref) <= 1e-8 * g_ref + 1e-12 * info["gnorm0"], tag + (info["gnorm"], g_ref)
+            assert abs(x[0] - unhex(case["x_first"])) <= 1e-8 and abs(x[n // 2] - unhex(case["x_mid"])) <= 1e-8, tag
+        assert info["gnorm"] <= case["tolerance"], tag
+
+
 def test_live_cuda_reference_side_by_side(gpu, oracle, cuda_golden):
     """The reference's CUDA solver and this library on the same device, same process, on inputs that are NOT in
     the golden file; plus one golden case re-run live (the .so is the program that produced the file)."""
