@@ -468,7 +468,7 @@ def largest_single_gpu_n(pkg, m):
     """Largest round n whose (2m+6)-vector arena (+ slack) fits the free memory of ONE GPU."""
     free, total = pkg.mem_info()
     per_elem = 8.0 * (2 * m + 6)
-    n = int((free - (6 << 30)) / per_elem)
+    n = int(0.88 * (free - (6 << 30)) / per_elem)  # head-room: the comparator must never drive the GPU out of memory
     return max(1_000_000, (n // 10_000_000) * 10_000_000)
 
 

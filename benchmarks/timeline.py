@@ -21,7 +21,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OPS = {-1: "x0", 0: "init", 1: "iter_begin", 2: "sg", 3: "l1", 4: "l2", 5: "ls_init", 6: "ls_step", 7: "accept",
-       8: "compact", 9: "compact_dir"}
+       8: "compact", 9: "compact_dir", 10: "f_init", 11: "f_accept", 12: "f_dir", 13: "f_fix", 14: "f_begin"}
 
 
 def load_pkg():

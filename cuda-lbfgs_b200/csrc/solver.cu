@@ -11,6 +11,7 @@
 // inlined-line-search variants.  There is no CPU fallback: without a CUDA device every compute
 // entry point returns LBFGSB200_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h> // header-only NVTX v3: no link dependency, a no-op unless a profiler is attached
 #include <math.h>
 #include <stdarg.h>
 #include <stdint.h>
@@ -234,6 +235,13 @@ struct ClassTimer {
 
 static bool is_multi(const lbfgsb200_solver *s) { return s->comm && s->comm->nranks > 1; }
 
+// NVTX ranges (nsys / ncu timelines): one per API call, and in the host-stepped loops one per phase of an iteration.
+// Inside a CUDA graph the phases are kernel nodes and show up by kernel name.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 // scalar step: on one GPU the scalar kernel sums the partials itself; on several the local sums
 // and halo values are packed, exchanged (NVLink mailboxes inside the scalar kernel, or one small NCCL
 // all-gather) and summed in rank order.
@@ -374,7 +382,11 @@ static int snapshot(lbfgsb200_solver *s)
 static int run_stepped(lbfgsb200_solver *s, int64_t iterations)
 {
     for (int64_t it = 0; it < iterations; ++it) {
-        LB_TRY(launch_direction(s));
+        {
+            NvtxRange r("lbfgsb200:direction");
+            LB_TRY(launch_direction(s));
+        }
+        NvtxRange r("lbfgsb200:line_search+accept");
         // line search: one fused evaluation + one device-side decision per trial
         do {
             {
@@ -446,14 +458,21 @@ static int run_stepped_fused(lbfgsb200_solver *s, int64_t iterations)
 {
     // s->h_ctrl is current: set_x0 / the previous run ended with a snapshot
     for (int64_t it = 0; it < iterations && !s->h_ctrl->done; ++it) {
-        if (s->h_ctrl->need_fix) LB_TRY(fused_fix_segment(s));
-        LB_TRY(fused_direction_segment(s));
-        LB_TRY(read_ctrl(s));
-        while (s->h_ctrl->ls_active && !s->h_ctrl->done) {
-            LB_TRY(fused_trial_segment(s));
+        {
+            NvtxRange r("lbfgsb200:direction+first_trial");
+            if (s->h_ctrl->need_fix) LB_TRY(fused_fix_segment(s));
+            LB_TRY(fused_direction_segment(s));
             LB_TRY(read_ctrl(s));
         }
+        {
+            NvtxRange r("lbfgsb200:line_search");
+            while (s->h_ctrl->ls_active && !s->h_ctrl->done) {
+                LB_TRY(fused_trial_segment(s));
+                LB_TRY(read_ctrl(s));
+            }
+        }
         if (s->h_ctrl->done) break;
+        NvtxRange r("lbfgsb200:accept+gram");
         LB_TRY(fused_accept_segment(s, 0));
         LB_TRY(read_ctrl(s));
         s->k_host += 1;
@@ -631,6 +650,7 @@ static int run_stepped_callback(lbfgsb200_solver *s, int64_t iterations)
 
 static int do_iterate(lbfgsb200_solver *s, int64_t iterations)
 {
+    NvtxRange nvtx_range("lbfgsb200:iterate");
     if (!s->x0_set) {
         set_error("iterate: set_x0 has not been called");
         return LBFGSB200_ERR_INVALID;
@@ -852,6 +872,7 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
 {
     if (!out) return LBFGSB200_ERR_INVALID;
     *out = nullptr;
+    NvtxRange nvtx_range("lbfgsb200:create");
     LB_TRY(check_params(params));
     if ((objective < 0 || objective > LBFGSB200_OBJ_TRIDIAG) && objective != LBFGSB200_OBJ_DEVICE_CALLBACK) { set_error("unknown objective %d", objective); return LBFGSB200_ERR_INVALID; }
     if (n_global == 0) { set_error("n must be > 0"); return LBFGSB200_ERR_INVALID; }
@@ -1386,6 +1407,7 @@ static int copy_vector(lbfgsb200_solver *s, double *dst, const double *src, size
 int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local)
 {
     if (!s || !x0_local) { set_error("set_x0: NULL argument"); return LBFGSB200_ERR_INVALID; }
+    NvtxRange nvtx_range("lbfgsb200:set_x0");
     // restore the pristine state (ring empty, pointers un-swapped), then evaluate f(x0), g(x0)
     DevState &st = s->h_snapshot;
     st.x = s->arena;
@@ -1484,6 +1506,7 @@ int lbfgsb200_iterate_profiled(lbfgsb200_solver_t *s, int64_t iterations,
 int lbfgsb200_get_x(lbfgsb200_solver_t *s, double *x_local_out)
 {
     if (!s || !x_local_out) return LBFGSB200_ERR_INVALID;
+    NvtxRange nvtx_range("lbfgsb200:get_x");
     LB_TRY(copy_vector(s, x_local_out, s->h_snapshot.x, s->n_local, false));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return 0;
