@@ -276,16 +276,16 @@ class Bench:
         self.barrier()  # ranks generate shards of different offsets (mt19937 skip-ahead): line up before any exchange
         return x0, n_local
 
-    def kernel_table(self, direction, m, V):
-        """algorithmic bytes per launch of each streaming-kernel class, steady state h = m"""
+    def kernel_table(self, flow, m, V):
+        """algorithmic bytes per launch of each streaming-kernel class (DESIGN.md section 4), steady state h = m;
+        flow = lbfgsb200_result_t.flow of the solver that ran (0 two-loop, 1 compact unfused, 2 compact fused)"""
         h = m
-        fused = direction == "compact" and os.environ.get("LBFGSB200_FUSED", "1") != "0"
-        if fused:
+        if flow == 2:
             # k_accept_gram: reads the 2(h-1) kept history rows + x, d, g_old, writes x, g, s, y
             # k_combine_trial: reads the 2h+1 basis vectors + x, writes d (the first line-search trial rides on it)
             return {"gram_rows": ("k_accept_gram", (2 * (h - 1) + 7) * V), "combine": ("k_combine_trial", (2 * h + 3) * V),
                     "trial": ("k_trial", 2 * V)}
-        if direction == "compact":
+        if flow == 1:
             return {"gram_rows": ("k_gram_tma2d", (2 * h + 1) * V), "combine": ("k_combine", (2 * h + 2) * V),
                     "trial": ("k_trial", 2 * V), "accept": ("k_accept", 7 * V)}
         return {"two_loop_pass": ("k_two_loop_pass", (8 * h - 1) * V / (2 * h)), "trial": ("k_trial", 2 * V), "accept": ("k_accept", 7 * V)}
@@ -323,7 +323,7 @@ class Bench:
         trials = float(np.sum(rows[:, 4])) if len(rows) else 0.0
         bytes_step = res["bytes_moved"] / K  # local shard, algorithmic
         out = {"value": K / (dev_ms / 1e3), "ms_per_step": dev_ms / K, "wall_ms_per_step": wall_ms / K,
-               "gpu_launches": int(launches), "trials_per_step": trials / K if K else None,
+               "gpu_launches": int(launches), "trials_per_step": trials / K if K else None, "flow": int(res["flow"]),
                "clocks": sampler.summary() if sampler else None}
         if sustain_s > 0:
             S = max(K, int(math.ceil(sustain_s / (dev_ms / K / 1e3))))
@@ -348,7 +348,7 @@ class Bench:
             res_p = solver.result()
             if self.rank == 0:
                 sys.stderr.write("kernel classes (%s): %s\n" % (direction, json.dumps(classes)))
-            table = self.kernel_table(direction, m, V)
+            table = self.kernel_table(res_p["flow"], m, V)
             kernels = {}
             for name, c in classes.items():
                 if name in table and c["launches"] > 0 and c["ms"] > 0:

@@ -80,6 +80,13 @@ def main():
         name = OPS.get(int(ops[i]), str(int(ops[i])))
         inside.setdefault(name, []).append((t_out[i] - t_in[i]) / 1e3)
         before.setdefault(name, []).append((t_in[i] - t_out[i - 1]) / 1e3)
+    # diagnostic sub-marks (op >= 100) carry clock64() in the t_in column: cycles between consecutive marks of an iteration
+    cyc = {}
+    for i in range(1, nrows):
+        if ops[i] >= 100 and ops[i - 1] >= 100:
+            cyc.setdefault("%d->%d" % (ops[i - 1], ops[i]), []).append(int(t_in[i] - t_in[i - 1]))
+    if cyc and rank == 0:
+        print(json.dumps({"cycles_between_marks": {k: float(np.median(v)) for k, v in cyc.items()}}), file=sys.stderr)
     total_us = (t_out[-1] - t_out[0]) / 1e3 if nrows > 1 else 0.0
     out = {"n_gpus": world, "n": args.size, "m": args.hist, "graph": args.graph, "iters": args.iters,
            "us_per_iteration": total_us / args.iters,

@@ -52,7 +52,7 @@ class Result(C.Structure):
     _fields_ = [("status", C.c_int), ("iterations", C.c_int64), ("trial_evals", C.c_int64),
                 ("kernel_launches", C.c_int64), ("f", C.c_double), ("gnorm", C.c_double),
                 ("device_ms", C.c_double), ("bytes_moved", C.c_double), ("f0", C.c_double),
-                ("gnorm0", C.c_double)]
+                ("gnorm0", C.c_double), ("flow", C.c_int), ("graph", C.c_int), ("num_gpus", C.c_int), ("reserved", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -84,7 +84,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = build_module.build()
+    path = os.environ.get("LBFGSB200_LIB") or build_module.build()  # LBFGSB200_LIB: an alternative build (kernel tuning A/B)
     L = C.CDLL(path)
     L.lbfgsb200_version.restype = C.c_int
     L.lbfgsb200_strerror.restype = C.c_char_p

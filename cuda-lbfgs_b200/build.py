@@ -39,6 +39,7 @@ def build(force=False, verbose=False):
     cmd = [nvcc_path()] + ccbin + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-O2,-pthread", "-shared",
            "-Xptxas", "-v" if verbose else "-O3"]
+    cmd += os.environ.get("LBFGSB200_BUILD_DEFS", "").split()  # e.g. "-DLB_AG_GROUPS=1" (kernel tuning experiments)
     cmd += [os.path.join(CSRC, f) for f in SOURCES]
     cmd += ["-ldl", "-lpthread", "-o", LIB]  # NCCL is dlopen()ed at run time (csrc/comm.cpp)
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -1,4 +1,4 @@
-// accept_gram.cuh -- the fused accept + pass-A kernel of the compact flow.
+// accept_gram.cuh -- the two streaming kernels of the fused compact flow (+ k_trial for further trials).
 //
 //   k_accept_gram    accept step at the alpha the line search returned (x_new, g_new, s, y, f) FUSED with pass A
 //                    of the NEXT direction (the 3 x (2h'+1) inner products of s_new, y_new, g_new with the new
@@ -8,22 +8,21 @@
 //                    instead of 3 + 4 (accept) + 2h' + 1 (pass A)  =>  3 vector streams fewer per iteration.
 //                    Replaces updateSolution + host grad + updateVectors + 2 D2D copies + ddot(g,g)
 //                    (par/L-BFGS.cu:309-347) and all 3h+3 cublasDdot calls of the next iteration (:219-267).
+//   k_combine_trial  pass B (d = -sum_j delta_j b_j, g.d) FUSED with the first line-search trial: every search starts at
+//                    alpha = INITIAL_STEP_SIZE (seq/line_search.cpp:21, :72, :138) and the neighbours' boundary d is known
+//                    before this pass (DevState::bL / bR), so f and grad f . d at x + step0 d cost one extra read of x
+//                    instead of a 2-stream trial pass, a launch and a scalar kernel.  Replaces 2h cublasDaxpy +
+//                    scaleByRho + negateVector (par/L-BFGS.cu:233-276) and the first updateSolution + host f/grad + ddot
+//                    of the search (par/L-BFGS-Wolfe.cu:276-311).
 //
-// HBM-bound stream; tensor cores are not used (FP64, ~1 flop/B).
-//
-// Three warp roles, one CTA per SM, kGramStages stages of shared memory:
-//   warp 0        producer: <= 7 tensor-map TMA loads per tile (kept S / Y rows in <= 2 runs each, x, d, g_old), ONE PER
-//                 LANE so that they issue together, into the next free stage; completion is counted in bytes on
-//                 full[stage]
-//   warps 1..4    accept: wait full[stage]; one double2 item per lane: x + alpha d, the three-point stencil by warp
-//                 shuffles (warp-edge lanes read the tile / the halo boxes), s, y, g_new, f; the x, d, g_old rows of the
-//                 stage are OVERWRITTEN IN PLACE with s, y, g_new, the four vectors are stored to HBM, ready[stage] is
-//                 raised.  They run ahead of the gram warps by up to the pipeline depth: the accept step of tile k+1
-//                 overlaps the inner products of tile k.
-//   warps 5..16   gram: wait ready[stage]; rows (s, y, g_new) x all columns of the new window, exactly the loop of
-//                 k_gram_tma2d; release the stage on empty[stage]
-// No CTA-wide barrier in the tile loop; the four accept warps meet in one named barrier per tile (between the reads of
-// their neighbours' x / d and the in-place writes).
+// HBM-bound streams; tensor cores are not used (FP64, ~1 flop/B).  Both are warp-specialised, one CTA per SM, with a ring
+// of NS <= kMaxStages shared-memory stages filled by tensor-map TMA (cp.async.bulk.tensor.2d, SASS UTMALDG.2D) and
+// mbarrier transaction counting.  Two things measured on the B200 shape them:
+//   * ONE thread issuing all boxes of a tile back to back is the bottleneck (~200 cycles per tensor-map TMA instruction):
+//     the boxes of a tile are issued by different LANES of the producer warp in the same cycle;
+//   * a stage of the ring is held for memory latency + the work of every warp role that touches it: the roles are
+//     pipelined over tiles (accept of tile k+1 overlaps the inner products of tile k), and k_combine_trial lets two
+//     consumer groups work on alternating tiles.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -34,8 +33,55 @@
 
 namespace lb {
 
-constexpr int kAgAcceptWarps = 4;
-constexpr int kAgGramWarps = kWsConsumerWarps - kAgAcceptWarps; // 12
+// stage / phase of a ring of NS mbarrier-guarded stages, advanced without integer division
+struct PipeState {
+    int stage;
+    unsigned phase;
+    __device__ __forceinline__ void advance(int by, int NS)
+    {
+        stage += by;
+        while (stage >= NS) {
+            stage -= NS;
+            phase ^= 1u;
+        }
+    }
+};
+__device__ __forceinline__ PipeState pipe_at(int first, int NS)
+{
+    PipeState p = {0, 0u};
+    p.advance(first, NS);
+    return p;
+}
+
+__device__ __forceinline__ void named_barrier_sync(int id, int threads)
+{
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory");
+}
+
+// ---- accept + pass A ------------------------------------------------------------------------------
+//   warp 0        producer: <= 11 tensor-map TMA loads per tile (kept S / Y rows in <= 2 runs each, x, d, g_old, four
+//                 2-element halo boxes), one per lane, into the next free stage; completion is counted in bytes on
+//                 full[stage]
+//   warps 1..4    accept (kAgGroups groups of 4 on alternating tiles; one group by default): wait full[stage]; one double2 item per lane: x + alpha d,
+//                 the three-point stencil by warp shuffles (warp-edge lanes read the tile, tile-edge lanes the halo
+//                 boxes), s, y, g_new, f; the x, d, g_old rows of the stage
+//                 are OVERWRITTEN IN PLACE with s, y, g_new, the four vectors are stored to HBM, ready[stage] is raised.
+//                 The groups run ahead of the gram warps by up to the pipeline depth.
+//   then 12       gram warps: wait ready[stage]; rows (s, y, g_new) x all columns of the new window, exactly the loop of
+//                 k_gram_tma2d; release the stage on empty[stage]
+// No CTA-wide barrier in the tile loop; the four warps of an accept group meet in one named barrier per tile (between
+// the reads of their neighbours' x / d and the in-place writes).
+constexpr int kAgGroupWarps = 4;                  // accept warps per group (4 x 32 lanes = the 128 items of a 256-wide tile)
+#ifndef LB_AG_GROUPS
+#define LB_AG_GROUPS 1
+#endif
+// accept groups working on alternating tiles (build-time tuning knob).  Measured on B200 at n = 1e8: 1 group 2.88-2.95 ms,
+// 2 groups 3.12-3.19 ms at m = 10; no difference at m = 3 -- the kernel is bound by the depth of the stage ring (a stage
+// is held for memory latency + accept + inner products), not by the accept rate, and extra warps only cost issue slots.
+constexpr int kAgGroups = LB_AG_GROUPS;
+constexpr int kAgAcceptWarps = kAgGroupWarps * kAgGroups;
+constexpr int kAgGramWarps = 12;
+constexpr int kAgThreads = 32 * (1 + kAgAcceptWarps + kAgGramWarps); // 672
 constexpr int kAgMaxCW = 9; // columns per gram warp: at most ceil((2*50+1) / 12)
 
 // Stage layout (doubles), T = tile width, hk = pairs kept from the old window (h if the ring is not full, else h-1:
@@ -45,32 +91,31 @@ constexpr int kAgMaxCW = 9; // columns per gram warp: at most ceil((2*50+1) / 12
 //   rows 0 .. hk-1        kept S rows, window order          (TMA, <= 2 boxes)
 //   rows hk .. 2hk-1      kept Y rows                        (TMA, <= 2 boxes)
 //   rows 2hk, +1, +2      x, d, g_old tiles (TMA)  ->  s_new, y_new, g_new after the accept warps
+//   then 4 halo slots     x[i0-2..i0-1], x[i0+T..i0+T+1], d[i0-2..i0-1], d[i0+T..i0+T+1]   (TMA, 2-column boxes; a
+//                         plain global load of these elements would put a DRAM round trip under load -- longer than
+//                         a whole tile takes -- on the accept warps' critical path)
+constexpr int kHaloSlotDoubles = 16; // one 128-byte aligned slot per halo box (TMA destinations are 128-byte aligned)
 __host__ __device__ inline size_t accept_gram_stage_doubles(int J, int T)
 {
-    return (size_t)J * T; // J = 2m+1 >= 2hk+3 rows
-}
-
-__device__ __forceinline__ void named_barrier_sync(int id, int threads)
-{
-    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory");
+    return (size_t)J * T + 4 * kHaloSlotDoubles; // J = 2m+1 >= 2hk+3 rows
 }
 
 template <class OBJ, int CW>
-__global__ void __launch_bounds__(kWsThreads, 1)
-k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ maps, int T, int init)
+__global__ void __launch_bounds__(kAgThreads, 1)
+k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ maps, int T, int NS, int init)
 {
     if (st->ctrl.done) return;
     extern __shared__ __align__(128) double tile[];
-    __shared__ __align__(8) unsigned long long full[kGramStages], ready[kGramStages], empty[kGramStages];
+    __shared__ __align__(8) unsigned long long full[kMaxStages], ready[kMaxStages], empty[kMaxStages];
     __shared__ double fsum[kAgAcceptWarps];
     const int h_old = init ? 0 : st->h;
     const int ks = (h_old == st->m) ? 1 : 0; // oldest pair evicted by the anticipated commit
     const int hk = h_old - ks, hp = hk + 1, J = 2 * hp + 1; // J columns of the new window
     const int nrow = 2 * hk + 3;                            // rows of a stage
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kGramStages; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&ready[s], kAgAcceptWarps);
+            mbar_init(&ready[s], kAgGroupWarps);
             mbar_init(&empty[s], kAgGramWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -82,20 +127,20 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
     const int mrow = 2 * st->m + 1;
     const size_t stage_doubles = accept_gram_stage_doubles(mrow, T);
     const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long tile_stride = (long long)gridDim.x * T; // elements between consecutive tiles of this CTA
     const int T2 = T >> 1;
     const int NE = T2 / 32 > 0 ? T2 / 32 : 1;     // element groups of 32 items (T >= 64)
-    const int NG = kAgGramWarps / NE;             // column groups: 3, 6 or 12
+    const int NG = kAgGramWarps / NE;             // column groups: 3, 4, 6 or 12
     double acc[CW][3];
 #pragma unroll
     for (int c = 0; c < CW; ++c) acc[c][0] = acc[c][1] = acc[c][2] = 0.0;
     double facc = 0.0;
-    const int gw = warp - 1 - kAgAcceptWarps, cg = gw % NG, eg = gw / NG; // gram-warp coordinates (warp >= 5)
+    const int gw = warp - 1 - kAgAcceptWarps, cg = gw % NG, eg = gw / NG; // gram-warp coordinates (warp >= 9)
 
     if (warp == 0) {
         // ---------------- producer ----------------
-        // One thread issuing every box of a tile back to back is the bottleneck (a tensor-map TMA instruction costs
-        // ~200 cycles to issue): lanes 0..6 each own ONE box of the tile and issue them in the same cycle.
         //   lane 0: S run A   1: Y run A   2: S run B   3: Y run B   4: x   5: d   6: g_old
+        //   lane 7: x left halo   8: x right halo   9: d left halo   10: d right halo   (2-column boxes)
         const int ns = st->nslots;
         const int a0 = (st->base + ks) % ns;          // physical slot of the first kept pair
         const int ra = min(hk, ns - a0), rb = hk - ra; // the kept window is at most two runs of slots
@@ -103,6 +148,7 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
         const CUtensorMap *map = &maps->run[1];
         int row = 0;
         size_t off = 0; // destination inside the stage, in doubles
+        int dcol = 0;   // column offset of the box relative to the tile
         bool valid = true;
         switch (lane) {
         case 0: map = &maps->run[ra]; row = kArenaRowS + a0; off = 0; valid = ra > 0; break;
@@ -112,22 +158,26 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
         case 4: row = row_x; off = (size_t)(2 * hk) * T; break;
         case 5: row = kArenaRowW; off = (size_t)(2 * hk + 1) * T; break;
         case 6: row = kArenaRowG; off = (size_t)(2 * hk + 2) * T; break;
+        case 7: map = &maps->halo; row = row_x; off = (size_t)mrow * T; dcol = -2; break;
+        case 8: map = &maps->halo; row = row_x; off = (size_t)mrow * T + kHaloSlotDoubles; dcol = T; break;
+        case 9: map = &maps->halo; row = kArenaRowW; off = (size_t)mrow * T + 2 * kHaloSlotDoubles; dcol = -2; break;
+        case 10: map = &maps->halo; row = kArenaRowW; off = (size_t)mrow * T + 3 * kHaloSlotDoubles; dcol = T; break;
         default: valid = false; break;
         }
-        const unsigned bytes = (unsigned)((size_t)nrow * T * sizeof(double));
-        for (long long k = 0; k < my_tiles; ++k) {
-            const int stage = (int)(k % kGramStages);
+        const unsigned bytes = (unsigned)(((size_t)nrow * T + 8) * sizeof(double));
+        PipeState ps = {0, 1u}; // the producer waits for the PREVIOUS use of a stage to be released
+        long long col = (long long)blockIdx.x * T;
+        for (long long k = 0; k < my_tiles; ++k, col += tile_stride, ps.advance(1, NS)) {
             if (lane == 0) {
-                if (k >= kGramStages) mbar_wait(&empty[stage], (unsigned)(((k / kGramStages) - 1) & 1));
-                mbar_expect_tx(&full[stage], bytes);
+                if (k >= NS) mbar_wait(&empty[ps.stage], ps.phase);
+                mbar_expect_tx(&full[ps.stage], bytes);
             }
             __syncwarp();
-            const int col = (int)((blockIdx.x + k * (long long)gridDim.x) * T);
-            if (valid) tma_load_2d(tile + stage * stage_doubles + off, map, col, row, &full[stage]);
+            if (valid) tma_load_2d(tile + ps.stage * stage_doubles + off, map, (int)col + dcol, row, &full[ps.stage]);
         }
     } else if (warp <= kAgAcceptWarps) {
-        // ---------------- accept warps ----------------
-        const int aw = warp - 1;
+        // ---------------- accept warps: group grp handles tiles grp, grp + 2, ... ----------------
+        const int grp = (warp - 1) / kAgGroupWarps, aw = (warp - 1) % kAgGroupWarps;
         const double alpha = init ? 0.0 : st->ls.alpha;
         const double xtL = st->xL + alpha * st->dL, xtR = st->xR + alpha * st->dR;
         const long long goff = st->goff, nglob = st->nglob;
@@ -138,32 +188,14 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
         double *__restrict__ y_out = st->Y + sp;
         const int e = aw * 32 + lane;   // double2 item of this lane within the tile
         const bool act = e < T2;
-        // The element just outside the tile (left of its first, right of its last element) is the only thing the
-        // stencil needs that the tile does not hold.  The one lane on each tile edge fetches it from global memory ONE
-        // TILE AHEAD into registers (x is not written by this kernel -- the new iterate goes to x_alt -- nor is d).
-        const bool edge_l = act && e == 0, edge_r = act && e == T2 - 1;
-        const double *__restrict__ gx = st->x;
-        const double *__restrict__ gd = st->w;
-        double hx = 0.0, hd = 0.0; // halo of the CURRENT tile (left for edge_l, right for edge_r)
-        auto halo_fetch = [&](long long k, double &ox, double &od) {
-            ox = od = 0.0;
-            if (k >= my_tiles || !(edge_l || edge_r)) return;
-            const long long col = (blockIdx.x + k * (long long)gridDim.x) * T;
-            const long long idx = edge_l ? col - 1 : col + T;
-            if (idx >= 0 && idx < n) {
-                ox = gx[idx];
-                od = gd[idx];
-            }
-        };
-        halo_fetch(0, hx, hd);
-        for (long long k = 0; k < my_tiles; ++k) {
-            const int stage = (int)(k % kGramStages);
-            double nx, nd;
-            halo_fetch(k + 1, nx, nd); // in flight while this tile is processed
-            mbar_wait(&full[stage], (unsigned)((k / kGramStages) & 1));
-            double *cur = tile + stage * stage_doubles;
+        long long col = ((long long)blockIdx.x + grp * (long long)gridDim.x) * T; // first element of the group's first tile
+        PipeState ps = pipe_at(grp, NS);
+        for (long long k = grp; k < my_tiles; k += kAgGroups, col += kAgGroups * tile_stride, ps.advance(kAgGroups, NS)) {
+            mbar_wait(&full[ps.stage], ps.phase);
+            double *cur = tile + ps.stage * stage_doubles;
             double *in_x = cur + (size_t)(2 * hk) * T, *in_d = in_x + T, *in_g = in_d + T;
-            const long long ge = (blockIdx.x + k * (long long)gridDim.x) * T + 2 * (long long)e; // first element of the item
+            const double *halo = cur + (size_t)mrow * T; // x[col-2..col-1], x[col+T..], d[col-2..col-1], d[col+T..]
+            const long long ge = col + 2 * (long long)e; // first element of the item
             double2 xc = make_double2(0.0, 0.0), dc = xc, go = xc;
             if (act) {
                 xc = reinterpret_cast<const double2 *>(in_x)[e];
@@ -181,18 +213,18 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
                         const int tl = 2 * e - 1; // tile coordinate of the left neighbour
                         if (ge == 0) l = xtL;
                         else if (tl >= 0) l = in_x[tl] + alpha * in_d[tl];
-                        else l = hx + alpha * hd; // edge_l
+                        else l = halo[1] + alpha * halo[2 * kHaloSlotDoubles + 1];
                     }
                     if (ge + 2 >= n) r = xtR;
                     else if (lane == 31) {
                         const int tr = 2 * e + 2;
                         if (tr < T) r = in_x[tr] + alpha * in_d[tr];
-                        else r = hx + alpha * hd; // edge_r
+                        else r = halo[kHaloSlotDoubles] + alpha * halo[3 * kHaloSlotDoubles];
                     }
                 }
             }
-            // every accept warp has read what it needs of its neighbours' x / d: the rows may now be overwritten
-            named_barrier_sync(1, 32 * kAgAcceptWarps);
+            // every warp of the group has read what it needs of its neighbours' x / d: the rows may now be overwritten
+            named_barrier_sync(1 + grp, 32 * kAgGroupWarps);
             if (act) {
                 double2 a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0; // elements beyond n contribute zeros
                 if (ge < n) {
@@ -229,10 +261,8 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
                 reinterpret_cast<double2 *>(in_d)[e] = a1; // y_new
                 reinterpret_cast<double2 *>(in_g)[e] = a2; // g_new
             }
-            hx = nx;
-            hd = nd;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&ready[stage]); // release: the three new rows of this stage are in place
+            if (lane == 0) mbar_arrive(&ready[ps.stage]); // release: the three new rows of this stage are in place
         }
     } else {
         // ---------------- gram warps ----------------
@@ -244,10 +274,10 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
         }
         const int e = eg * 32 + lane;
         const bool act = e < T2;
-        for (long long k = 0; k < my_tiles; ++k) {
-            const int stage = (int)(k % kGramStages);
-            mbar_wait(&ready[stage], (unsigned)((k / kGramStages) & 1));
-            const double2 *cur2 = reinterpret_cast<const double2 *>(tile + stage * stage_doubles);
+        PipeState ps = {0, 0u};
+        for (long long k = 0; k < my_tiles; ++k, ps.advance(1, NS)) {
+            mbar_wait(&ready[ps.stage], ps.phase);
+            const double2 *cur2 = reinterpret_cast<const double2 *>(tile + ps.stage * stage_doubles);
             if (act) {
                 const double2 a0 = cur2[(size_t)(2 * hk) * T2 + e], a1 = cur2[(size_t)(2 * hk + 1) * T2 + e],
                               a2 = cur2[(size_t)(2 * hk + 2) * T2 + e];
@@ -262,7 +292,7 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]); // this warp is done reading the stage
+            if (lane == 0) mbar_arrive(&empty[ps.stage]); // this warp is done reading the stage
         }
     }
     __syncthreads(); // all tiles consumed; the tile storage can be reused for the reduction
@@ -284,7 +314,7 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
         if (lane == 0) fsum[warp - 1] = fw;
     }
     __syncthreads();
-    for (int q = threadIdx.x; q < J * 3; q += kWsThreads) {
+    for (int q = threadIdx.x; q < J * 3; q += kAgThreads) {
         double s = 0.0;
         for (int g = 0; g < NE; ++g) s += red[g * (J * 3) + q];
         st->partials[(size_t)q * gridDim.x + blockIdx.x] = s;
@@ -297,42 +327,42 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
 }
 
 // ---- pass B + first trial ------------------------------------------------------------------------
-//   k_combine_trial  pass B (d = -sum_j delta_j b_j, g.d) FUSED with the first line-search trial: every search starts at
-//                    alpha = INITIAL_STEP_SIZE (seq/line_search.cpp:21, :72, :138) and the neighbours' boundary d is known
-//                    before this pass (DevState::bL / bR), so f and grad f . d at x + step0 d cost one extra read of x
-//                    instead of a 2-stream trial pass, a launch and a scalar kernel.  Replaces 2h cublasDaxpy +
-//                    scaleByRho + negateVector (par/L-BFGS.cu:233-276) and the first updateSolution + host f/grad + ddot
-//                    of the search (par/L-BFGS-Wolfe.cu:276-311).
-// Same producer / consumer skeleton as above: warp 0 issues <= 6 tensor-map TMA loads per tile (S and Y in <= 2 runs
-// each, g, x), one per lane; 4 consumer warps take one double2 item per lane, run the fma chain over the 2h+1 columns
-// out of shared memory (window-column order: the chain k_combine uses, so d has the same bits), store d, form the trial
-// point and evaluate the stencil by warp shuffles, warp-edge values going through a small shared-memory exchange and ONE
-// named barrier per tile.  Tiles OVERLAP by 4 elements on each side (TMA box of T columns every T-8 elements): the
-// halo of the stencil comes with the tile, recomputed with the same chain; the overlap is requested by neighbouring CTAs
-// at the same time and is served by L2.
-constexpr int kCtWarps = 4;
+// Warp 0 issues <= 6 tensor-map TMA loads per tile (S and Y in <= 2 runs each, g, x), one per lane; two groups of 4
+// consumer warps take alternating tiles, one double2 item per lane: the fma chain over the 2h+1 columns out of shared
+// memory (window-column order: the chain k_combine uses, so d has the same bits), the store of d, the trial point, the
+// stencil by warp shuffles, warp-edge values going through a small shared-memory exchange and ONE named barrier per
+// tile and group.  Tiles OVERLAP by halo2 items on each side (a TMA box of T columns every T - 4 halo2 elements): the halo
+// of the stencil comes with the tile, recomputed with the same chain; the overlap is requested by neighbouring CTAs at the
+// same time and is served by L2.  halo2 = 4 keeps every box 64-byte aligned (measured best on B200: 2 -> 2.80 ms,
+// 4 -> 2.72 ms, 8 -> 2.74 ms at n = 1e8, m = 10).
+constexpr int kCtGroupWarps = 4;
+#ifndef LB_CT_GROUPS
+#define LB_CT_GROUPS 2
+#endif
+constexpr int kCtGroups = LB_CT_GROUPS; // consumer groups on alternating tiles (2: 2.75 ms, 1: 2.81 ms at n = 1e8, m = 10)
+constexpr int kCtWarps = kCtGroupWarps * kCtGroups;
 constexpr int kCtThreads = 32 * (kCtWarps + 1);
-constexpr int kCtHaloItems = 2; // double2 items of overlap on each side of a tile (keeps the d stores 32-byte aligned)
+constexpr int kCtHaloItems = 4; // default double2 items of overlap on each side of a tile
 
 __host__ __device__ inline size_t combine_trial_stage_doubles(int m, int T) { return (size_t)(2 * m + 2) * T; }
 
 template <class OBJ>
 __global__ void __launch_bounds__(kCtThreads, 1)
-k_combine_trial(const DevState *__restrict__ st, const ArenaMaps *__restrict__ maps, int T)
+k_combine_trial(const DevState *__restrict__ st, const ArenaMaps *__restrict__ maps, int T, int NS, int halo2)
 {
     if (st->ctrl.done) return;
     extern __shared__ __align__(128) double tile[];
-    __shared__ __align__(8) unsigned long long full[kGramStages], empty[kGramStages];
+    __shared__ __align__(8) unsigned long long full[kMaxStages], empty[kMaxStages];
     __shared__ double coef[kMaxCols];
-    __shared__ __align__(16) double2 xs[2][32 * kCtWarps]; // trial values of the tile, for the warp-edge lanes
+    __shared__ __align__(16) double2 xs[kCtGroups][2][32 * kCtGroupWarps]; // trial values of a tile, for the warp-edge lanes
     const int h = st->h;
     const bool steep = st->steepest || h == 0;
     const int J = steep ? 1 : 2 * h + 1; // d = -g is the combination with the single coefficient 1 on g
     for (int j = threadIdx.x; j < J; j += kCtThreads) coef[j] = steep ? 1.0 : st->delta[j];
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kGramStages; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kCtWarps);
+            mbar_init(&empty[s], kCtGroupWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -340,10 +370,11 @@ k_combine_trial(const DevState *__restrict__ st, const ArenaMaps *__restrict__ m
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long n = st->n;
     const long long nvec_pad = (n + 1) >> 1;
-    const int T2 = T >> 1, own2 = T2 - 2 * kCtHaloItems; // items per tile / items owned per tile
+    const int T2 = T >> 1, own2 = T2 - 2 * halo2; // items per tile / items owned per tile (halo2 items of overlap per side)
     const long long ntiles = (nvec_pad + own2 - 1) / own2;
     const size_t stage_doubles = combine_trial_stage_doubles(st->m, T);
     const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long item_stride = (long long)gridDim.x * own2; // items between consecutive tiles of this CTA
     double a_gd = 0.0, a_f = 0.0, a_gdt = 0.0;
 
     if (warp == 0) {
@@ -366,33 +397,33 @@ k_combine_trial(const DevState *__restrict__ st, const ArenaMaps *__restrict__ m
         default: valid = false; break;
         }
         const unsigned bytes = (unsigned)((size_t)(2 * hh + 2) * T * sizeof(double));
-        for (long long k = 0; k < my_tiles; ++k) {
-            const int stage = (int)(k % kGramStages);
+        PipeState ps = {0, 1u};
+        long long first = (long long)blockIdx.x * own2 - halo2; // first item of the tile (negative for the very first: zero-filled)
+        for (long long k = 0; k < my_tiles; ++k, first += item_stride, ps.advance(1, NS)) {
             if (lane == 0) {
-                if (k >= kGramStages) mbar_wait(&empty[stage], (unsigned)(((k / kGramStages) - 1) & 1));
-                mbar_expect_tx(&full[stage], bytes);
+                if (k >= NS) mbar_wait(&empty[ps.stage], ps.phase);
+                mbar_expect_tx(&full[ps.stage], bytes);
             }
             __syncwarp();
-            const long long tl = blockIdx.x + k * (long long)gridDim.x;
-            const int col = (int)(2 * (tl * own2 - kCtHaloItems)); // first element of the tile (-4 for the first tile: zero-filled)
-            if (valid) tma_load_2d(tile + stage * stage_doubles + off, map, col, row, &full[stage]);
+            if (valid) tma_load_2d(tile + ps.stage * stage_doubles + off, map, (int)(2 * first), row, &full[ps.stage]);
         }
     } else {
-        const int cwp = warp - 1;
+        const int grp = (warp - 1) / kCtGroupWarps, cwp = (warp - 1) % kCtGroupWarps;
         const int e = cwp * 32 + lane; // item of this lane within the tile
         const bool in_tile = e < T2;
-        const bool owner = in_tile && e >= kCtHaloItems && e < T2 - kCtHaloItems;
+        const bool owner = in_tile && e >= halo2 && e < T2 - halo2;
         const int hh = steep ? 0 : h;
         const double alpha = st->lsp.step0; // every search starts at INITIAL_STEP_SIZE
         const double xtL = st->xL + alpha * st->dL, xtR = st->xR + alpha * st->dR;
         const long long goff = st->goff, nglob = st->nglob;
         double *__restrict__ w = st->w;
-        for (long long k = 0; k < my_tiles; ++k) {
-            const int stage = (int)(k % kGramStages);
-            mbar_wait(&full[stage], (unsigned)((k / kGramStages) & 1));
-            const double2 *cur2 = reinterpret_cast<const double2 *>(tile + stage * stage_doubles);
-            const long long tl = blockIdx.x + k * (long long)gridDim.x;
-            const long long i = tl * own2 - kCtHaloItems + e; // global item index (may be < 0 or beyond the vector: zeros)
+        PipeState ps = pipe_at(grp, NS);
+        long long first = ((long long)blockIdx.x + grp * (long long)gridDim.x) * own2 - halo2;
+        int buf = 0;
+        for (long long k = grp; k < my_tiles; k += kCtGroups, first += kCtGroups * item_stride, ps.advance(kCtGroups, NS), buf ^= 1) {
+            mbar_wait(&full[ps.stage], ps.phase);
+            const double2 *cur2 = reinterpret_cast<const double2 *>(tile + ps.stage * stage_doubles);
+            const long long i = first + e; // global item index (may be < 0 or beyond the vector: zeros)
             double2 s = make_double2(0.0, 0.0), gv = s, xv = s;
             if (in_tile) {
 #pragma unroll 4
@@ -415,11 +446,11 @@ k_combine_trial(const DevState *__restrict__ st, const ArenaMaps *__restrict__ m
             const double2 xt = make_double2(xv.x + alpha * s.x, xv.y + alpha * s.y);
             double l = 0.0, r = 0.0;
             if (OBJ::kStencil) {
-                double2 *xb = xs[k & 1];
-                xb[e < 32 * kCtWarps ? e : 0] = xt;
+                double2 *xb = xs[grp][buf];
+                xb[e] = xt;
                 l = __shfl_up_sync(0xffffffffu, xt.y, 1);
                 r = __shfl_down_sync(0xffffffffu, xt.x, 1);
-                named_barrier_sync(2, 32 * kCtWarps);
+                named_barrier_sync(1 + grp, 32 * kCtGroupWarps);
                 if (lane == 0 && e > 0) l = xb[e - 1].y;
                 if (lane == 31 && e + 1 < T2) r = xb[e + 1].x;
             }
@@ -439,7 +470,7 @@ k_combine_trial(const DevState *__restrict__ st, const ArenaMaps *__restrict__ m
                 a_gdt += q0 * s.x + q1 * s.y;
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (lane == 0) mbar_arrive(&empty[ps.stage]);
         }
     }
     __syncthreads();
@@ -457,17 +488,8 @@ k_combine_trial(const DevState *__restrict__ st, const ArenaMaps *__restrict__ m
     }
 }
 
-typedef void (*combine_trial_kernel_t)(const DevState *, const ArenaMaps *, int);
-inline combine_trial_kernel_t combine_trial_kernel_for(int objective)
-{
-    switch (objective) {
-    case LBFGSB200_OBJ_QUADRATIC: return k_combine_trial<ObjQuadratic>;
-    case LBFGSB200_OBJ_ROSENBROCK: return k_combine_trial<ObjRosenbrock>;
-    default: return k_combine_trial<ObjTridiag>;
-    }
-}
-
-typedef void (*accept_gram_kernel_t)(const DevState *, const ArenaMaps *, int, int);
+typedef void (*accept_gram_kernel_t)(const DevState *, const ArenaMaps *, int, int, int);
+typedef void (*combine_trial_kernel_t)(const DevState *, const ArenaMaps *, int, int, int);
 
 // columns per gram warp for history size m and tile width T (the kernel derives the same NG from T)
 inline int accept_gram_cw(int m, int T)
@@ -483,6 +505,14 @@ inline accept_gram_kernel_t accept_gram_kernel_for(int objective)
     case LBFGSB200_OBJ_QUADRATIC: return k_accept_gram<ObjQuadratic, CW>;
     case LBFGSB200_OBJ_ROSENBROCK: return k_accept_gram<ObjRosenbrock, CW>;
     default: return k_accept_gram<ObjTridiag, CW>;
+    }
+}
+inline combine_trial_kernel_t combine_trial_kernel_for(int objective)
+{
+    switch (objective) {
+    case LBFGSB200_OBJ_QUADRATIC: return k_combine_trial<ObjQuadratic>;
+    case LBFGSB200_OBJ_ROSENBROCK: return k_combine_trial<ObjRosenbrock>;
+    default: return k_combine_trial<ObjTridiag>;
     }
 }
 

@@ -33,10 +33,14 @@ __device__ __forceinline__ void reduce_partials(const double *__restrict__ parti
     double v[kMaxQ];
 #pragma unroll
     for (int q = 0; q < kMaxQ; ++q) v[q] = 0.0;
+    // (the batch of loads of all quantities is issued before the first add: one round trip to L2 per 256 partials)
     for (int i = threadIdx.x; i < grid; i += kScalarThreads) {
+        double t[kMaxQ];
+#pragma unroll
+        for (int q = 0; q < kMaxQ; ++q) t[q] = (q < nq) ? partials[(size_t)q * grid + i] : 0.0;
 #pragma unroll
         for (int q = 0; q < kMaxQ; ++q)
-            if (q < nq) v[q] += partials[(size_t)q * grid + i];
+            if (q < nq) v[q] += t[q];
     }
 #pragma unroll
     for (int q = 0; q < kMaxQ; ++q) {
@@ -492,6 +496,7 @@ __device__ void fused_accept(DevState *st, int op, int from_comm, int nparts, do
         __syncthreads();
     } else {
         gram_rows_from_partials(st->partials, nparts, nrows, nrows + 4, rows);
+        tl_mark(st, 101, global_ns()); // (diagnostic timeline: partial sums done)
         if (from_comm == 2) {
             if (threadIdx.x == 0 && st->n > 0) { // the accept kernel wrote the new iterate to x_alt
                 rows[nrows + 0] = st->x_alt[0];
@@ -603,10 +608,12 @@ __device__ void fused_accept(DevState *st, int op, int from_comm, int nparts, do
         }
     }
     __syncthreads();
+    tl_mark(st, 102, global_ns()); // (bookkeeping done)
     if (s_flags[1]) {
         compact_recursion(st, rows, dyn, s_flags[0], true);
         __syncthreads();
     }
+    tl_mark(st, 103, global_ns()); // (Gram update + recursion done)
     if (threadIdx.x == 0) {
         if (st->steepest) { // d = -g: the neighbours' boundary d follows from their boundary g
             st->dL = -st->gL;

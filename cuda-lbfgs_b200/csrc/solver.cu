@@ -154,8 +154,10 @@ struct lbfgsb200_solver {
     int gram_T = 512;           // compact form: elements per vector per shared-memory tile
     int gram_tma = 0, gram_NG = 2, gram_NS = 2, gram_G = 1; // stand-alone pass A: tensor-map TMA (2, default) or cp.async pipeline (0)
     size_t gram_smem = 0;
-    ArenaMaps *arena_maps = nullptr; // device: tensor maps over the arena (TMA pass A, fused accept + pass A)
-    ArenaMaps arena_maps_host;       // staging copy (the upload is stream-ordered)
+    ArenaMaps *arena_maps = nullptr;    // device: tensor maps over the arena, boxes gram_T wide (pass A, fused accept + pass A)
+    ArenaMaps *arena_maps_ct = nullptr; // device: the same with boxes ct_T wide (k_combine_trial)
+    ArenaMaps arena_maps_host[2];       // staging copies (the uploads are stream-ordered)
+    int ct_T = 256, ct_NS = 4, ct_halo = kCtHaloItems; // k_combine_trial: tile width, stages, overlap
     double *gram = nullptr;     // compact form: Gram matrix + pass-A rows + delta + all-gather buffer
     // fused compact flow (accept_gram.cuh): k_accept_gram + k_combine_trial
     bool fused = false;
@@ -194,6 +196,7 @@ struct lbfgsb200_solver {
     bool x0_set = false;
     int64_t k_host = 0; // accepts launched so far: an upper bound on the device's h
     int64_t launches = 0;
+    bool last_graph = false;
     double last_ms = 0.0;
     double streams_at_start = 0.0; // vec_streams when the last timed region began
     double streams_last = 0.0;
@@ -276,9 +279,9 @@ static void launch_gram(lbfgsb200_solver *s)
     const size_t smem = s->gram_smem;
     if (s->gram_tma == 2) {
         if ((2 * m + 1 + s->gram_NG - 1) / s->gram_NG <= 7)
-            k_gram_tma2d<7><<<s->grid_gram, kWsThreads, smem, s->stream>>>(s->d_st, s->arena_maps, s->gram_T, s->gram_NG);
+            k_gram_tma2d<7><<<s->grid_gram, kWsThreads, smem, s->stream>>>(s->d_st, s->arena_maps, s->gram_T, s->gram_NG, s->gram_NS);
         else
-            k_gram_tma2d<kMaxCW><<<s->grid_gram, kWsThreads, smem, s->stream>>>(s->d_st, s->arena_maps, s->gram_T, s->gram_NG);
+            k_gram_tma2d<kMaxCW><<<s->grid_gram, kWsThreads, smem, s->stream>>>(s->d_st, s->arena_maps, s->gram_T, s->gram_NG, s->gram_NS);
     } else {
         const int G = s->gram_G, per = (2 * m + 1 + G - 1) / G, cwg = (per + kGramWarps - 1) / kGramWarps;
         const dim3 grid(s->grid_gram, G);
@@ -418,7 +421,7 @@ static int run_stepped(lbfgsb200_solver *s, int64_t iterations)
 static void launch_accept_gram(lbfgsb200_solver *s, int init)
 {
     ClassTimer t(s, KC_GRAM);
-    s->ag_kernel<<<s->grid_ag, kWsThreads, s->ag_smem, s->stream>>>(s->d_st, s->arena_maps, s->gram_T, init);
+    s->ag_kernel<<<s->grid_ag, kAgThreads, s->ag_smem, s->stream>>>(s->d_st, s->arena_maps, s->gram_T, s->gram_NS, init);
     s->launches += 1;
 }
 
@@ -432,7 +435,7 @@ static int fused_direction_segment(lbfgsb200_solver *s)
 {
     {
         ClassTimer t(s, KC_COMBINE);
-        s->ct_kernel<<<s->grid_combine, kCtThreads, s->ct_smem, s->stream>>>(s->d_st, s->arena_maps, s->gram_T);
+        s->ct_kernel<<<s->grid_combine, kCtThreads, s->ct_smem, s->stream>>>(s->d_st, s->arena_maps_ct, s->ct_T, s->ct_NS, s->ct_halo);
         s->launches += 1;
     }
     return scalar_step(s, OP_F_DIR, 0, PACK_NONE);
@@ -657,6 +660,7 @@ static int do_iterate(lbfgsb200_solver *s, int64_t iterations)
     }
     s->streams_at_start = s->h_snapshot.vec_streams;
     const bool graph = wants_graph(s);
+    s->last_graph = graph;
     if (graph && !s->graph_exec) LB_TRY(build_graph(s));
     if (s->graph_exec) { // cudaGraphSetConditional is only legal inside the graph: gate it per run
         s->cond_flag = graph ? 1 : 0;
@@ -775,7 +779,7 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int build_arena_maps(lbfgsb200_solver *s, ArenaMaps *dev_dst)
+static int build_arena_maps(lbfgsb200_solver *s, ArenaMaps *dev_dst, int box_T, int staging)
 {
     static encode_tiled_fn encode = nullptr; // the entry point is process-wide
     if (!encode) {
@@ -790,7 +794,7 @@ static int build_arena_maps(lbfgsb200_solver *s, ArenaMaps *dev_dst)
         encode = (encode_tiled_fn)fn;
     }
     const int rows_total = 4 + 2 * s->nslots;
-    ArenaMaps *host = &s->arena_maps_host;
+    ArenaMaps *host = &s->arena_maps_host[staging];
     memset(host, 0, sizeof *host);
     auto make = [&](CUtensorMap *out, int box_cols, int box_rows) -> bool {
         const cuuint64_t gdim[2] = {(cuuint64_t)s->stride, (cuuint64_t)rows_total};
@@ -803,7 +807,7 @@ static int build_arena_maps(lbfgsb200_solver *s, ArenaMaps *dev_dst)
         return r == CUDA_SUCCESS;
     };
     bool ok = true;
-    for (int r = 1; r <= s->nslots && ok; ++r) ok = make(&host->run[r], s->gram_T, r);
+    for (int r = 1; r <= s->nslots && ok; ++r) ok = make(&host->run[r], box_T, r);
     ok = ok && make(&host->halo, 2, 1);
     if (!ok) return LBFGSB200_ERR_CUDA;
     // (the host copy lives in the solver: the upload is stream-ordered)
@@ -904,6 +908,7 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     s->grid_accept = pick_grid((long long)s->n_local, s->sms, params->grid_ctas, kCtasPerSmAccept);
     const bool compact = params->direction == LBFGSB200_DIR_COMPACT;
     const int J = 2 * params->m + 1;
+    size_t budget_bytes = (size_t)216 * 1024; // shared memory of the TMA kernels (LBFGSB200_GRAM_TMA_KB)
     if (compact) {
         // Pass A, stand-alone (user objectives; fused flow: only after a rejected pair), LBFGSB200_GRAM_TMA forces one:
         //   2  tensor-map TMA (UTMALDG.2D): <= 5 tiled loads per tile of the whole history (default)
@@ -917,16 +922,36 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
         s->fused = s->gram_tma == 2 && objective != LBFGSB200_OBJ_DEVICE_CALLBACK && !(ef && atoi(ef) == 0);
         int Jt = J;
         if (s->gram_tma) {
-            // ONE CTA per SM owning (almost) all of shared memory: kGramStages stages of the largest tile that
-            // fits, so kGramStages-1 whole tiles per SM are in flight.  The fused kernel's stage carries 3 more rows
-            // (x, d, g_old inputs next to the s, y, g_new it forms) and the halo slots; both kernels share T.
+            // ONE CTA per SM owning (almost) all of shared memory: NS stages of T-wide tiles of every row, so NS-1
+            // whole tiles per SM are in flight.  Wide tiles amortise the per-tile costs (barriers, TMA issue, the
+            // overlap of k_combine_trial), deep rings hide latency: the widest tile that still leaves 3 stages is
+            // taken, then 2 stages of 256 (a TMA box dimension is at most 256 elements).  LBFGSB200_AG_TILE /
+            // LBFGSB200_CT_TILE = "T,NS" force a configuration (tuning knobs).
             const char *eb = getenv("LBFGSB200_GRAM_TMA_KB");
             const size_t budget = (size_t)(eb ? atoi(eb) : 216) * 1024;
-            s->gram_NS = kGramStages;
-            s->gram_T = 256; // a TMA box dimension is at most 256 elements
-            while (s->gram_T > 32 && (size_t)s->gram_NS * combine_trial_stage_doubles(params->m, s->gram_T) * sizeof(double) > budget) s->gram_T >>= 1;
+            budget_bytes = budget;
+            auto pick_tile = [&](size_t rows, const char *envname, int *T_out, int *NS_out) {
+                // measured on B200 (benchmarks/tile_sweep.sh, n = 1e8): 2 stages of 256 beat 3 of 192 beat 4 of 128
+                // (m = 20: 86.6 / 83.3 / 79.8 it/s), so the widest tile with >= 2 stages wins
+                static const int widths[] = {256, 192, 128, 64};
+                int T = 64, NS = 2;
+                for (int w : widths) {
+                    const int ns = (int)(budget / (rows * (size_t)w * sizeof(double)));
+                    if (ns >= 2) { T = w; NS = ns > kMaxStages ? kMaxStages : ns; break; }
+                }
+                if (const char *e = getenv(envname)) {
+                    int t = 0, n2 = 0;
+                    if (sscanf(e, "%d,%d", &t, &n2) == 2 && t >= 64 && t <= 256 && t % 64 == 0 && n2 >= 2 && n2 <= kMaxStages &&
+                        rows * (size_t)t * sizeof(double) * (size_t)n2 <= budget + 8192) { T = t; NS = n2; }
+                }
+                *T_out = T;
+                *NS_out = NS;
+            };
+            pick_tile((size_t)J, "LBFGSB200_AG_TILE", &s->gram_T, &s->gram_NS);
+            pick_tile((size_t)J + 1, "LBFGSB200_CT_TILE", &s->ct_T, &s->ct_NS); // one row more: x
+            if (const char *e = getenv("LBFGSB200_CT_HALO")) s->ct_halo = atoi(e) >= 1 && 2 * atoi(e) < s->ct_T / 4 ? atoi(e) : kCtHaloItems;
             s->ag_smem = (size_t)s->gram_NS * accept_gram_stage_doubles(J, s->gram_T) * sizeof(double);
-            s->ct_smem = (size_t)s->gram_NS * combine_trial_stage_doubles(params->m, s->gram_T) * sizeof(double); // one row more: x
+            s->ct_smem = (size_t)s->ct_NS * combine_trial_stage_doubles(params->m, s->ct_T) * sizeof(double);
         } else {
             // cp.async pipeline.  Large tiles matter (per-tile barrier/issue overhead): split the basis
             // into G column groups of <= ~40 columns (+3 row vectors when G > 1), take the largest T
@@ -960,12 +985,36 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
         s->grid_ag = s->grid_gram;
         if (s->fused) {
             const int cw = accept_gram_cw(params->m, s->gram_T);
-            if (s->gram_T < 64 || cw > kAgMaxCW) s->fused = false; // the fused kernel's warp layout needs tiles of >= 64 elements
-            else {
+            // The fused kernels pay per-tile costs (the overlap of k_combine_trial, the accept warps' latency) that only
+            // 256-wide tiles amortise, and the 12 gram warps of k_accept_gram hold at most kAgMaxCW columns each: the
+            // fused flow runs for m <= 13 (J = 2m+1 <= 27 columns in 3 column groups).  Above that the unfused flow --
+            // stand-alone pass A with 16 consumer warps + register-streaming k_combine -- is the faster one (measured at
+            // n = 1e8: m = 20: 93.9 vs 86.6 it/s with 128-wide fused tiles; m = 50: 41.3 vs 26.9).
+            // LBFGSB200_FUSED=1 forces the fused flow where it can run at all.
+            const bool force = ef && atoi(ef) == 1;
+            if (s->gram_T < 64 || cw > kAgMaxCW || (!force && (s->gram_T < 256 || s->ct_T < 256))) s->fused = false;
+        }
+        if (s->gram_tma && !s->fused) {
+            // the stand-alone pass A keeps its own tile policy: 4 stages of the widest power-of-two tile that fits
+            s->gram_NS = kMaxStages;
+            s->gram_T = 256;
+            while (s->gram_T > 32 && (size_t)s->gram_NS * J * s->gram_T * sizeof(double) > budget_bytes) s->gram_T >>= 1;
+            s->gram_smem = (size_t)s->gram_NS * J * s->gram_T * sizeof(double);
+            int NE2 = s->gram_T / 2 / 32;
+            if (NE2 < 1) NE2 = 1;
+            if (NE2 > kWsConsumerWarps / 2) NE2 = kWsConsumerWarps / 2;
+            s->gram_NG = kWsConsumerWarps / NE2;
+            while (s->gram_NG < kWsConsumerWarps && (J + s->gram_NG - 1) / s->gram_NG > kMaxCW) s->gram_NG <<= 1;
+            const long long tiles2 = ((long long)s->n_local + s->gram_T - 1) / s->gram_T;
+            s->grid_gram = params->grid_ctas > 0 ? params->grid_ctas : (int)(tiles2 < s->sms ? (tiles2 < 1 ? 1 : tiles2) : s->sms);
+        }
+        if (s->fused) {
+            {
+                const int cw = accept_gram_cw(params->m, s->gram_T);
                 s->ag_kernel = cw <= 7 ? accept_gram_kernel_for<7>(objective) : accept_gram_kernel_for<kAgMaxCW>(objective);
                 s->ct_kernel = combine_trial_kernel_for(objective);
-                // k_combine_trial: one CTA per SM over tiles that own T/2 - 4 double2 items each
-                const long long own2 = s->gram_T / 2 - 2 * kCtHaloItems;
+                // k_combine_trial: one CTA per SM over tiles that own T/2 - 2 halo double2 items each
+                const long long own2 = s->ct_T / 2 - 2 * s->ct_halo;
                 const long long ct_tiles = (((long long)s->n_local + 1) / 2 + own2 - 1) / own2;
                 s->grid_combine = params->grid_ctas > 0 ? params->grid_ctas : (int)(ct_tiles < s->sms ? ct_tiles : s->sms);
             }
@@ -1032,7 +1081,7 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     const size_t off_part = off;      off = align_up(off + sizeof(double) * npart, 256);
     const size_t off_pkt = off;       off = align_up(off + sizeof(double) * kPacket * (size_t)(nranks + 1), 256);
     const size_t off_gram = off;      off = align_up(off + sizeof(double) * s->gram_doubles, 256);
-    const size_t off_maps = off;      off = align_up(off + (compact && s->gram_tma ? sizeof(ArenaMaps) : 0), 256);
+    const size_t off_maps = off;      off = align_up(off + (compact && s->gram_tma ? 2 * sizeof(ArenaMaps) : 0), 256);
     const size_t off_trace = off;     off = align_up(off + sizeof(double) * LBFGSB200_TRACE_COLS * trace_rows, 256);
     int tl_cap = 0;
     if (const char *et = getenv("LBFGSB200_TIMELINE")) tl_cap = atoi(et) > 0 ? atoi(et) : 0;
@@ -1045,7 +1094,10 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     s->partials = (double *)(aux + off_part);
     s->pkt = (double *)(aux + off_pkt);
     if (s->gram_doubles) s->gram = (double *)(aux + off_gram);
-    if (compact && s->gram_tma) s->arena_maps = (ArenaMaps *)(aux + off_maps);
+    if (compact && s->gram_tma) {
+        s->arena_maps = (ArenaMaps *)(aux + off_maps);
+        s->arena_maps_ct = s->arena_maps + 1;
+    }
     if (trace_rows) s->trace = (double *)(aux + off_trace);
     if (tl_cap) s->timeline = (unsigned long long *)(aux + off_tl);
     if (compact) {
@@ -1140,7 +1192,10 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     st.status = LBFGSB200_RUNNING;
     st.tl_cap = tl_cap;
     st.tl = s->timeline;
-    if (s->arena_maps) CREATE_RC(build_arena_maps(s, s->arena_maps));
+    if (s->arena_maps) {
+        CREATE_RC(build_arena_maps(s, s->arena_maps, s->gram_T, 0));
+        CREATE_RC(build_arena_maps(s, s->arena_maps_ct, s->ct_T, 1));
+    }
     CREATE_TRY(cudaMemcpyAsync(s->d_st, &st, sizeof st, cudaMemcpyHostToDevice, s->stream));
     // no synchronisation here: everything above is ordered on the solver stream, which every later call uses
 #undef CREATE_TRY
@@ -1526,6 +1581,10 @@ int lbfgsb200_get_result(lbfgsb200_solver_t *s, lbfgsb200_result_t *r)
     r->bytes_moved = s->streams_last * 8.0 * (double)s->n_local;
     r->f0 = st.f0;
     r->gnorm0 = sqrt(st.gg0);
+    r->flow = s->params.direction == LBFGSB200_DIR_TWO_LOOP ? 0 : (s->fused ? 2 : 1);
+    r->graph = s->last_graph ? 1 : 0;
+    r->num_gpus = s->comm ? s->comm->nranks : 1;
+    r->reserved = 0;
     return 0;
 }
 

@@ -134,6 +134,11 @@ typedef struct {
     double bytes_moved;  /* algorithmic HBM bytes of that region (bytes model) */
     double f0;           /* f(x0) and ||grad f(x0)||: the reference's "Iteration 0" line (seq/lbfgs.cpp:77-78) */
     double gnorm0;
+    int flow;            /* which kernels ran: 0 explicit two-loop, 1 compact (pass A, combine, trial, accept as separate
+                          * kernels), 2 compact fused (k_accept_gram + k_combine_trial; m <= 25 with the built-in objectives) */
+    int graph;           /* 1: the iterations of the last call ran as one CUDA graph */
+    int num_gpus;        /* GPUs the solve ran on */
+    int reserved;
 } lbfgsb200_result_t;
 
 typedef struct lbfgsb200_solver lbfgsb200_solver_t; /* one per GPU / rank */

@@ -31,6 +31,8 @@ for stage in "$@"; do
          [ $N -ge 2 ] && timeout 200 $T --nproc-per-node $N --master-port 29601 benchmarks/timeline.py --gpus $N --size $((12500000*N)) 2>/dev/null | grep '^{' >> $O/timeline.jsonl
          cat $O/timeline.jsonl | cut -c1-900 ;;
     multi8) timeout 900 python -m pytest tests/test_gpu_multi.py -q -k "every_device or one_process" > $O/pytest_multi8.log 2>&1; echo "rc=$?"; tail -8 $O/pytest_multi8.log ;;
+    ncu20) B="python bench.py --hist 20 --steps 4 --warmup 3 --no-cpu-baseline --single-variant --sustain 0 --graph 0"
+         ncu --set full --clock-control none -k regex:"k_accept_gram|k_combine_trial" -s 50 -c 4 -o $O/prof20 $B > $O/ncu20.log 2>&1; ls -la $O/prof20* ;;
     *) echo "unknown stage $stage" ;;
   esac
 done

@@ -41,7 +41,7 @@ def test_traces_match_reference_golden(gpu, golden, direction):
             # the rounding of the terms it is summed from, not of the residue
             assert abs(info["f"] - unhex(want["f"])) <= tol * abs(unhex(want["f"])) + 1e-15 * info["f0"], \
                 (name, K, info["f"], unhex(want["f"]))
-            assert abs(info["gnorm"] - unhex(want["gnorm"])) <= max(tol, 1e-9) * unhex(want["gnorm"]) + 1e-13 * info["gnorm0"], (name, K)
+            assert abs(info["gnorm"] - unhex(want["gnorm"])) <= 1e-8 * unhex(want["gnorm"]), (name, K)  # BASELINE.json's bar for |g|
             for got, key in ((x[0], "x_first"), (x[n // 2], "x_mid"), (x[-1], "x_last")):
                 ref = unhex(want[key])
                 assert abs(got - ref) <= tol * max(abs(ref), 1e-3), (name, K, key, got, ref)
