@@ -66,7 +66,7 @@ _lib = None
 
 # every symbol include/lbfgsb200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "lbfgsb200_create_callback", "lbfgsb200_checkpoint_save", "lbfgsb200_checkpoint_load", "lbfgsb200_version", "lbfgsb200_strerror", "lbfgsb200_last_error", "lbfgsb200_device_count",
+    "lbfgsb200_create_callback", "lbfgsb200_create_callback_sharded", "lbfgsb200_device_halo", "lbfgsb200_checkpoint_save", "lbfgsb200_checkpoint_load", "lbfgsb200_version", "lbfgsb200_strerror", "lbfgsb200_last_error", "lbfgsb200_device_count",
     "lbfgsb200_params_default", "lbfgsb200_solve", "lbfgsb200_create", "lbfgsb200_set_x0",
     "lbfgsb200_iterate", "lbfgsb200_iterate_profiled", "lbfgsb200_get_x", "lbfgsb200_get_result",
     "lbfgsb200_get_trace", "lbfgsb200_local_size", "lbfgsb200_destroy", "lbfgsb200_shard_range",
@@ -98,6 +98,10 @@ def lib():
                                    C.c_void_p, C.c_size_t]
     L.lbfgsb200_create_callback.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Params),
                                             C.c_size_t]
+    L.lbfgsb200_create_callback_sharded.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Params),
+                                                    C.c_void_p, C.c_size_t]
+    L.lbfgsb200_device_halo.restype = C.c_void_p
+    L.lbfgsb200_device_halo.argtypes = [C.c_void_p]
     L.lbfgsb200_set_x0.argtypes = [C.c_void_p, C.c_void_p]
     L.lbfgsb200_checkpoint_save.argtypes = [C.c_void_p, C.c_char_p]
     L.lbfgsb200_checkpoint_load.argtypes = [C.c_void_p, C.c_char_p]
@@ -281,12 +285,16 @@ class Solver:
         self.params = params
         self.trace_rows = trace_rows
         if objective == "callback":
-            _check(lib().lbfgsb200_create_callback(C.byref(self.h), callback, user, n_global, C.byref(params),
-                                                   trace_rows), "create_callback")
+            _check(lib().lbfgsb200_create_callback_sharded(C.byref(self.h), callback, user, n_global, C.byref(params),
+                                                           comm.h if comm else None, trace_rows), "create_callback")
         else:
             _check(lib().lbfgsb200_create(C.byref(self.h), OBJ[objective], n_global, C.byref(params),
                                           comm.h if comm else None, trace_rows), "create")
         self.n_local = lib().lbfgsb200_local_size(self.h)
+
+    def device_halo(self):
+        """device address of { xL, xR, dL, dR, gL, gR } (lbfgsb200_device_halo): what a sharded user objective reads"""
+        return lib().lbfgsb200_device_halo(self.h)
 
     def set_x0(self, x0):
         """x0: numpy array (host) or int device pointer holding this rank's shard."""

@@ -704,9 +704,9 @@ k_accept_generic(const DevState *__restrict__ st, const double *__restrict__ g_n
 {
     if (st->ctrl.done) return;
     const double alpha = init ? 0.0 : st->ls.alpha;
-    const double *__restrict__ x = st->x;
+    const double *x = st->x; // (user objectives: x_alt == x, the iterate is updated in place -- no __restrict__)
     const double *__restrict__ d = st->w;
-    double *__restrict__ xw = st->x_alt;
+    double *xw = st->x_alt;
     double *gw = st->g;
     const size_t sp = (size_t)spare_slot(*st) * (size_t)st->stride;
     double *__restrict__ s_out = st->S + sp;

@@ -14,6 +14,7 @@
 #include <nvtx3/nvToolsExt.h> // header-only NVTX v3: no link dependency, a no-op unless a profiler is attached
 #include <math.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -174,7 +175,7 @@ struct lbfgsb200_solver {
     lbfgsb200_fg_device_fn cb = nullptr;     // user device objective (lbfgsb200_create_callback)
     void *cb_user = nullptr;
     double *cb_buf = nullptr;                // g_trial [stride] + {f, g.d, g.g} + a device zero
-    double *x_cur = nullptr;                 // host mirror of DevState::x (the accept step swaps x / x_alt)
+    bool cb_graph_failed = false;            // the callback could not be stream-captured: host-stepped loop instead
     accept_kernel_t accept_kernel = nullptr;
 
     double *arena = nullptr;    // x, x_alt, g, w, S[nslots], Y[nslots]
@@ -413,6 +414,60 @@ static int run_stepped(lbfgsb200_solver *s, int64_t iterations)
     return 0;
 }
 
+// ---- user (callback) objectives ----------------------------------------------------------------
+// The callback replaces k_trial (one call per line-search trial) and the evaluation half of the accept kernel (one
+// more call at the accepted step, followed by k_accept_generic).  x is updated IN PLACE for these solvers
+// (DevState::x_alt == x: the generic accept kernel is element-wise), so every pointer the callback receives is the
+// same in every iteration and the calls can be recorded into the CUDA graph like the built-in kernels.
+static int callback_eval(lbfgsb200_solver *s, const double *d_alpha, double *d_out3)
+{
+    if (s->cb(s->arena, s->h_snapshot.w, d_alpha, s->cb_buf, d_out3, s->n_local, s->offset, s->cb_user, s->stream)) {
+        set_error("the objective callback failed");
+        return LBFGSB200_ERR_INVALID;
+    }
+    return 0;
+}
+
+static int callback_trial_segment(lbfgsb200_solver *s)
+{
+    {
+        ClassTimer t(s, KC_TRIAL);
+        LB_TRY(callback_eval(s, &s->d_st->ls.alpha, s->partials));
+    }
+    return scalar_step(s, OP_LS_STEP, 0, PACK_NONE, 1); // the 3 sums of this shard are final: one "partial" each
+}
+
+static int callback_accept_segment(lbfgsb200_solver *s, int init)
+{
+    double *scal = s->cb_buf + s->stride, *d_zero = scal + 4;
+    {
+        // gradient and f at the accepted step (the last trial may have been at another alpha)
+        ClassTimer t(s, KC_ACCEPT);
+        LB_TRY(callback_eval(s, init ? d_zero : &s->d_st->ls.alpha, scal));
+        k_accept_generic<<<s->grid, kThreads, 0, s->stream>>>(s->d_st, s->cb_buf, scal, init);
+        s->launches += 1;
+    }
+    return scalar_step(s, init ? OP_INIT : OP_ACCEPT, 0, PACK_ACCEPT, s->grid);
+}
+
+// host-stepped loop for user objectives that cannot be captured (or use_graph = 0)
+static int run_stepped_callback(lbfgsb200_solver *s, int64_t iterations)
+{
+    for (int64_t it = 0; it < iterations; ++it) {
+        LB_TRY(launch_direction(s));
+        LB_TRY(read_ctrl(s));
+        while (s->h_ctrl->ls_active && !s->h_ctrl->done) {
+            LB_TRY(callback_trial_segment(s));
+            LB_TRY(read_ctrl(s));
+        }
+        if (s->h_ctrl->done) break;
+        LB_TRY(callback_accept_segment(s, 0));
+        s->k_host += 1;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // ---- fused compact flow (accept_gram.cuh) ---------------------------------------------------------
 //   [ stand-alone pass A + OP_F_FIX, only after a rejected pair with a full ring ]
 //   k_combine_trial (d, g.d, first trial)      -> OP_F_DIR    (safeguard, search start, first decision)
@@ -517,7 +572,7 @@ static int capture_segment(lbfgsb200_solver *s, cudaGraph_t g, std::vector<cudaG
     const cudaGraphNode_t *deps = nullptr;
     size_t ndeps = 0;
     cudaError_t e = cudaStreamGetCaptureInfo_v2(s->stream, &status, nullptr, nullptr, &deps, &ndeps);
-    if (e == cudaSuccess) tail.assign(deps, deps + ndeps);
+    if (e == cudaSuccess && status == cudaStreamCaptureStatusActive) tail.assign(deps, deps + ndeps);
     cudaGraph_t out = nullptr;
     cudaError_t e2 = cudaStreamEndCapture(s->stream, &out);
     s->stream = run_stream;
@@ -565,6 +620,11 @@ static int build_graph(lbfgsb200_solver *s)
     std::vector<cudaGraphNode_t> top_tail, tail;
     cudaGraph_t iter_body = nullptr, trial_body = nullptr;
     const int64_t k_saved = s->k_host, l_saved = s->launches;
+    struct Restore { // recording counts launches and pretends the history is full: undo both on every exit
+        lbfgsb200_solver *s;
+        int64_t k, l;
+        ~Restore() { s->k_host = k; s->launches = l; }
+    } restore{s, k_saved, l_saved};
     if (s->fused) {
         LB_TRY(capture_segment(s, s->graph, top_tail, [&]() { return scalar_step(s, OP_F_BEGIN, 0, PACK_NONE); }));
         LB_TRY(add_conditional(s->graph, top_tail, h_outer, cudaGraphCondTypeWhile, &iter_body));
@@ -585,10 +645,12 @@ static int build_graph(lbfgsb200_solver *s)
         LB_TRY(add_conditional(iter_body, tail, h_inner, cudaGraphCondTypeWhile, &trial_body));
         std::vector<cudaGraphNode_t> inner_tail;
         LB_TRY(capture_segment(s, trial_body, inner_tail, [&]() {
+            if (s->cb) return callback_trial_segment(s); // the user's kernels become nodes of the loop body
             s->trial_kernel<<<s->grid, kThreads, 0, s->stream>>>(s->d_st);
             return scalar_step(s, OP_LS_STEP, 0, PACK_NONE);
         }));
         LB_TRY(capture_segment(s, iter_body, tail, [&]() {
+            if (s->cb) return callback_accept_segment(s, 0);
             s->accept_kernel<<<s->grid_accept, kThreads, 0, s->stream>>>(s->d_st, 0);
             s->launches += 1;
             return scalar_step(s, OP_ACCEPT, 0, PACK_ACCEPT);
@@ -596,17 +658,63 @@ static int build_graph(lbfgsb200_solver *s)
         // fixed part = everything captured except the two nodes of the trial loop body
         s->graph_fixed_launches = (s->launches - l_saved) - 1; // scalar_step of the trial body counted once; k_trial not counted
     }
-    s->k_host = k_saved;
-    s->launches = l_saved;
     GRAPH_TRY(cudaGraphInstantiate(&s->graph_exec, s->graph, 0));
     return 0;
 }
 
 static bool wants_graph(const lbfgsb200_solver *s)
 {
-    // graph mode: not instrumented, no user callbacks, and on several GPUs only with the peer-to-peer exchange,
-    // whose kernels are ordinary graph nodes (NCCL calls and event pairs stay on the stepped path)
-    return s->params.use_graph && !s->profiling && !s->cb && !(is_multi(s) && !s->comm->p2p);
+    // graph mode: not instrumented, and on several GPUs only with the peer-to-peer exchange, whose kernels are
+    // ordinary graph nodes (NCCL calls and event pairs stay on the stepped path).  A user objective runs in the graph
+    // when its callback could be stream-captured (kernel launches / async copies on the stream it is given).
+    return s->params.use_graph && !s->profiling && !s->cb_graph_failed && !(is_multi(s) && !s->comm->p2p);
+}
+
+// Can the user's callback be recorded?  One evaluation is captured into a throw-away graph: the capture must
+// survive (a callback that synchronises, allocates with cudaMalloc or touches the legacy stream invalidates it) and
+// may only have produced what a conditional-node body accepts -- kernel, memcpy, memset and empty nodes (no
+// stream-ordered allocations, host functions or event nodes).
+static bool callback_is_capturable(lbfgsb200_solver *s)
+{
+    cudaStream_t run_stream = s->stream;
+    if (cudaStreamBeginCapture(s->capture_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    s->stream = s->capture_stream;
+    const int rc = callback_eval(s, &s->d_st->ls.alpha, s->partials);
+    s->stream = run_stream;
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(s->capture_stream, &g);
+    bool ok = rc == 0 && e == cudaSuccess && g != nullptr;
+    if (ok) {
+        size_t count = 0;
+        ok = cudaGraphGetNodes(g, nullptr, &count) == cudaSuccess && count > 0;
+        std::vector<cudaGraphNode_t> nodes(count);
+        if (ok) ok = cudaGraphGetNodes(g, nodes.data(), &count) == cudaSuccess;
+        for (size_t i = 0; ok && i < count; ++i) {
+            cudaGraphNodeType type;
+            ok = cudaGraphNodeGetType(nodes[i], &type) == cudaSuccess &&
+                 (type == cudaGraphNodeTypeKernel || type == cudaGraphNodeTypeMemcpy || type == cudaGraphNodeTypeMemset ||
+                  type == cudaGraphNodeTypeEmpty);
+        }
+    }
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    return ok;
+}
+
+// Builds the graph if this run wants one.  A user callback that cannot be recorded makes the solver fall back, once
+// and for good, to the host-stepped loop, which has no such restriction.
+static int ensure_graph(lbfgsb200_solver *s)
+{
+    if (!wants_graph(s) || s->graph_exec) return 0;
+    if (s->cb && !callback_is_capturable(s)) {
+        s->cb_graph_failed = true;
+        if (getenv("LBFGSB200_VERBOSE")) fprintf(stderr, "lbfgsb200: the objective callback cannot be stream-captured: host-stepped loop\n");
+        return 0;
+    }
+    return build_graph(s);
 }
 
 static int run_graph(lbfgsb200_solver *s, int64_t iterations)
@@ -618,39 +726,6 @@ static int run_graph(lbfgsb200_solver *s, int64_t iterations)
     return 0;
 }
 
-// host-stepped loop for user (callback) objectives: the callback is launched by the host, so the
-// host has to know after every decision whether another evaluation is wanted
-static int run_stepped_callback(lbfgsb200_solver *s, int64_t iterations)
-{
-    double *g_trial = s->cb_buf, *scal = s->cb_buf + s->stride;
-    const double *d_alpha = &s->d_st->ls.alpha;
-    for (int64_t it = 0; it < iterations; ++it) {
-        LB_TRY(launch_direction(s));
-        LB_TRY(read_ctrl(s));
-        while (s->h_ctrl->ls_active && !s->h_ctrl->done) {
-            if (s->cb(s->x_cur, s->h_snapshot.w, d_alpha, g_trial, s->partials, s->n_local, 0, s->cb_user, s->stream)) {
-                set_error("the objective callback failed");
-                return LBFGSB200_ERR_INVALID;
-            }
-            LB_TRY(scalar_step(s, OP_LS_STEP, 0, PACK_NONE, 1)); // the 3 sums are already final: one "partial" each
-            LB_TRY(read_ctrl(s));
-        }
-        if (s->h_ctrl->done) break;
-        // gradient and f at the accepted step (the last trial may have been at another alpha)
-        if (s->cb(s->x_cur, s->h_snapshot.w, d_alpha, g_trial, scal, s->n_local, 0, s->cb_user, s->stream)) {
-            set_error("the objective callback failed");
-            return LBFGSB200_ERR_INVALID;
-        }
-        k_accept_generic<<<s->grid, kThreads, 0, s->stream>>>(s->d_st, g_trial, scal, 0);
-        s->launches += 1;
-        LB_TRY(scalar_step(s, OP_ACCEPT, 0, PACK_ACCEPT, s->grid));
-        s->x_cur = (s->x_cur == s->arena) ? s->arena + s->stride : s->arena;
-        s->k_host += 1;
-    }
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
-
 static int do_iterate(lbfgsb200_solver *s, int64_t iterations)
 {
     NvtxRange nvtx_range("lbfgsb200:iterate");
@@ -659,9 +734,9 @@ static int do_iterate(lbfgsb200_solver *s, int64_t iterations)
         return LBFGSB200_ERR_INVALID;
     }
     s->streams_at_start = s->h_snapshot.vec_streams;
+    LB_TRY(ensure_graph(s));
     const bool graph = wants_graph(s);
     s->last_graph = graph;
-    if (graph && !s->graph_exec) LB_TRY(build_graph(s));
     if (s->graph_exec) { // cudaGraphSetConditional is only legal inside the graph: gate it per run
         s->cond_flag = graph ? 1 : 0;
         CUDA_TRY(cudaMemcpyAsync(&s->d_st->cond_outer, s->cond_handles, sizeof s->cond_handles, cudaMemcpyHostToDevice, s->stream));
@@ -686,7 +761,7 @@ static int do_iterate(lbfgsb200_solver *s, int64_t iterations)
             // an exit at the top of / inside an iteration (converged, line search failed) still ran that
             // iteration's nodes as no-ops; "maximum iterations" is raised by the last accept itself
             const bool extra = s->h_snapshot.ctrl.done && s->h_snapshot.status != LBFGSB200_MAX_ITER;
-            s->launches += (its + (extra ? 1 : 0)) * s->graph_fixed_launches + 2 * trials;
+            s->launches += (its + (extra ? 1 : 0)) * s->graph_fixed_launches + (s->cb ? 1 : 2) * trials; // (the user's own kernels are not counted)
         }
         s->k_host += its;
     }
@@ -996,7 +1071,7 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
         }
         if (s->gram_tma && !s->fused) {
             // the stand-alone pass A keeps its own tile policy: 4 stages of the widest power-of-two tile that fits
-            s->gram_NS = kMaxStages;
+            s->gram_NS = kGramStages;
             s->gram_T = 256;
             while (s->gram_T > 32 && (size_t)s->gram_NS * J * s->gram_T * sizeof(double) > budget_bytes) s->gram_T >>= 1;
             s->gram_smem = (size_t)s->gram_NS * J * s->gram_T * sizeof(double);
@@ -1227,11 +1302,11 @@ void lbfgsb200_destroy(lbfgsb200_solver_t *s)
     delete s;
 }
 
-int lbfgsb200_create_callback(lbfgsb200_solver_t **out, lbfgsb200_fg_device_fn fn, void *user, size_t n,
-                              const lbfgsb200_params_t *params, size_t trace_rows)
+int lbfgsb200_create_callback_sharded(lbfgsb200_solver_t **out, lbfgsb200_fg_device_fn fn, void *user, size_t n_global,
+                                      const lbfgsb200_params_t *params, lbfgsb200_comm_t *comm, size_t trace_rows)
 {
     if (!fn) { set_error("create_callback: fn is NULL"); return LBFGSB200_ERR_INVALID; }
-    int rc = lbfgsb200_create(out, LBFGSB200_OBJ_DEVICE_CALLBACK, n, params, nullptr, trace_rows);
+    int rc = lbfgsb200_create(out, LBFGSB200_OBJ_DEVICE_CALLBACK, n_global, params, comm, trace_rows);
     if (rc < 0) return rc;
     lbfgsb200_solver *s = *out;
     s->cb = fn;
@@ -1246,6 +1321,19 @@ int lbfgsb200_create_callback(lbfgsb200_solver_t **out, lbfgsb200_fg_device_fn f
         return LBFGSB200_ERR_NOMEM;
     }
     return 0;
+}
+
+int lbfgsb200_create_callback(lbfgsb200_solver_t **out, lbfgsb200_fg_device_fn fn, void *user, size_t n,
+                              const lbfgsb200_params_t *params, size_t trace_rows)
+{
+    return lbfgsb200_create_callback_sharded(out, fn, user, n, params, nullptr, trace_rows);
+}
+
+const double *lbfgsb200_device_halo(const lbfgsb200_solver_t *s)
+{
+    // DevState keeps xL, xR, dL, dR, gL, gR as six consecutive doubles (state.h)
+    static_assert(offsetof(DevState, gR) - offsetof(DevState, xL) == 5 * sizeof(double), "halo block layout");
+    return s ? &s->d_st->xL : nullptr;
 }
 
 size_t lbfgsb200_local_size(const lbfgsb200_solver_t *s) { return s ? s->n_local : 0; }
@@ -1327,7 +1415,8 @@ int lbfgsb200_checkpoint_load(lbfgsb200_solver_t *s, const char *path)
     const int rank = s->comm ? s->comm->rank : 0, nranks = s->comm ? s->comm->nranks : 1;
     if (!rc && (h.n_local != s->n_local || h.stride != s->stride || h.m != s->params.m || h.objective != s->objective ||
                 h.direction != s->params.direction || h.profile != s->params.profile || h.rank != rank || h.nranks != nranks ||
-                h.gram_doubles != gram_doubles_of(s) || h.trace_rows != s->trace_rows || st.fused != s->h_snapshot.fused)) {
+                h.gram_doubles != gram_doubles_of(s) || h.trace_rows != s->trace_rows || st.fused != s->h_snapshot.fused ||
+                (s->cb && h.x_is_alt))) { // (user objectives keep x in place)
         set_error("checkpoint_load: the checkpoint was written by a solver of a different shape");
         rc = LBFGSB200_ERR_INVALID;
     }
@@ -1353,7 +1442,7 @@ int lbfgsb200_checkpoint_load(lbfgsb200_solver_t *s, const char *path)
     const DevState &cur = s->h_snapshot;
     st.arena0 = s->arena;
     st.x = h.x_is_alt ? s->arena + s->stride : s->arena;
-    st.x_alt = h.x_is_alt ? s->arena : s->arena + s->stride;
+    st.x_alt = s->cb ? st.x : (h.x_is_alt ? s->arena : s->arena + s->stride);
     st.g = cur.g; st.w = cur.w; st.S = cur.S; st.Y = cur.Y;
     st.partials = cur.partials; st.send = cur.send; st.recv = cur.recv; st.trace = cur.trace;
     st.gram = cur.gram; st.gram_rows = cur.gram_rows; st.gram_recv = cur.gram_recv; st.delta = cur.delta;
@@ -1370,7 +1459,6 @@ int lbfgsb200_checkpoint_load(lbfgsb200_solver_t *s, const char *path)
     CUDA_TRY(cudaMemcpyAsync(s->d_st, &s->h_snapshot, sizeof(DevState), cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     s->k_host = h.k_host;
-    s->x_cur = st.x;
     s->x0_set = true;
     return 0;
 }
@@ -1466,7 +1554,7 @@ int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local)
     // restore the pristine state (ring empty, pointers un-swapped), then evaluate f(x0), g(x0)
     DevState &st = s->h_snapshot;
     st.x = s->arena;
-    st.x_alt = s->arena + s->stride;
+    st.x_alt = s->cb ? s->arena : s->arena + s->stride; // user objectives: x is updated in place
     st.base = 0;
     st.h = 0;
     st.k = 0;
@@ -1487,7 +1575,7 @@ int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local)
     CUDA_TRY(cudaMemsetAsync(st.w, 0, s->stride * sizeof(double), s->stream)); // d = 0
     // record the graph while the upload is in flight (recording executes nothing; it has its own stream)
     s->profiling = false;
-    if (wants_graph(s) && !s->graph_exec) LB_TRY(build_graph(s));
+    LB_TRY(ensure_graph(s));
     if (is_multi(s)) {
         // neighbours' boundary x before the first evaluation (one-element halo)
         if (s->comm->p2p) {
@@ -1501,15 +1589,7 @@ int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local)
         }
     }
     if (s->cb) {
-        double *g_trial = s->cb_buf, *scal = s->cb_buf + s->stride, *d_zero = scal + 4;
-        if (s->cb(st.x, st.w, d_zero, g_trial, scal, s->n_local, 0, s->cb_user, s->stream)) {
-            set_error("the objective callback failed");
-            return LBFGSB200_ERR_INVALID;
-        }
-        k_accept_generic<<<s->grid, kThreads, 0, s->stream>>>(s->d_st, g_trial, scal, 1);
-        s->launches += 1;
-        LB_TRY(scalar_step(s, OP_INIT, 0, PACK_ACCEPT, s->grid));
-        s->x_cur = s->arena + s->stride; // OP_INIT swapped x and x_alt
+        LB_TRY(callback_accept_segment(s, 1));
     } else if (s->fused) {
         LB_TRY(fused_accept_segment(s, 1));
     } else {

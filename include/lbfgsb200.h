@@ -78,8 +78,9 @@ typedef enum {
  * (seq/lbfgs.h:18-19).  Evaluate at the trial point x + (*d_alpha)*d WITHOUT materialising it:
  * write grad f there to g_out[0..n) and { f, grad.d, grad.grad } to d_out3[0..3) (all device
  * memory; d_alpha is a DEVICE scalar, so no host synchronisation is needed).  Enqueue everything
- * on cuda_stream (a cudaStream_t) and return 0, or non-zero to abort the solve.
- * lbfgsb200_dot() / lbfgsb200_nrm2() may be used for the reductions. */
+ * on cuda_stream (a cudaStream_t) and return 0, or non-zero to abort the solve.  n is the number of elements this
+ * solver owns, global_offset the global index of the first (0 unless the solver is sharded).
+ * lbfgsb200_dot() / lbfgsb200_nrm2() may be used for the reductions (host-stepped loop only: they allocate). */
 typedef int (*lbfgsb200_fg_device_fn)(const double *x, const double *d, const double *d_alpha,
                                       double *g_out, double *d_out3, size_t n, size_t global_offset,
                                       void *user, void *cuda_stream);
@@ -177,11 +178,30 @@ int lbfgsb200_resolve_num_gpus(int requested, size_t n);
 int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
                      const lbfgsb200_params_t *params, lbfgsb200_comm_t *comm,
                      size_t trace_rows);
-/* Same, with a user device objective instead of a built-in one (single GPU, host-stepped loop;
- * two-loop or compact direction, all line searches).  fn is called once per line-search trial and
- * once more at the accepted step. */
+/* Same, with a user device objective instead of a built-in one (two-loop or compact direction, all line searches).
+ * fn is called once per line-search trial and once more at the accepted step.  With params.use_graph (the default)
+ * the calls are RECORDED: fn runs once per call site while the solver captures its CUDA graph, and the kernels /
+ * async copies it enqueued on the stream it was given are replayed from the device for every evaluation (the pointer
+ * arguments are the same in every iteration; alpha is read from *d_alpha on the device).  A callback that cannot be
+ * captured (it synchronises, allocates -- lbfgsb200_dot / lbfgsb200_nrm2 allocate their scratch -- or works on
+ * another stream without joining it back) makes the solver fall back to its host-stepped loop, where fn is called by
+ * the host before every evaluation; use_graph = 0 selects that loop outright. */
 int lbfgsb200_create_callback(lbfgsb200_solver_t **out, lbfgsb200_fg_device_fn fn, void *user,
                               size_t n, const lbfgsb200_params_t *params, size_t trace_rows);
+/* The same on a sharded solver (comm != NULL: this rank owns lbfgsb200_shard_range(n_global, rank, nranks)).  fn gets
+ * this rank's shard (x, d, g_out: n_local elements; global_offset = index of its first element) and writes the
+ * PARTIAL sums { f, grad.d, grad.grad } of its shard to d_out3; the solver adds them over the ranks in rank order.
+ * An objective that couples neighbouring elements reads the neighbours' boundary values from
+ * lbfgsb200_device_halo(). */
+int lbfgsb200_create_callback_sharded(lbfgsb200_solver_t **out, lbfgsb200_fg_device_fn fn, void *user,
+                                      size_t n_global, const lbfgsb200_params_t *params,
+                                      lbfgsb200_comm_t *comm, size_t trace_rows);
+/* DEVICE pointer to six doubles { xL, xR, dL, dR, gL, gR }: the LAST element of the left neighbour's shard and the
+ * FIRST element of the right neighbour's, of the current iterate x, the search direction d and the gradient g
+ * (zeros where there is no neighbour).  Refreshed by the solver once per iteration before fn is called, so the
+ * neighbours' trial-point values are xL + alpha*dL and xR + alpha*dR.  Valid for the life of the solver; read it
+ * from device code only (a kernel the callback launches). */
+const double *lbfgsb200_device_halo(const lbfgsb200_solver_t *s);
 /* x0: this rank's shard (n_local doubles), host or device pointer.  Evaluates f(x0), grad f(x0)
  * (seq/lbfgs.cpp:28-30). */
 int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local);

@@ -6,6 +6,10 @@
 // library knows nothing about it.
 //   cb_rosenbrock : the chained Rosenbrock of parallel-implementation/functions.cpp:26-49
 //                   (same expression order as the built-in, so results can be compared)
+//   cb_rosenbrock_sharded : the same on one shard of a multi-GPU solver -- partial sums of the shard, neighbours'
+//                   boundary values from lbfgsb200_device_halo()
+//   cb_rosenbrock_syncing : cb_rosenbrock + a cudaStreamSynchronize: legal in the host-stepped loop, impossible to
+//                   capture -- the solver must fall back by itself
 //   cb_dense      : f = x^T A x + b^T x with a dense SPD A (the reference's unused fixtures,
 //                   sequential-implementation/matrices.h)
 #include <cuda_runtime.h>
@@ -56,6 +60,32 @@ __global__ void rosen_eval(const double *x, const double *d, const double *d_alp
     tgg[i] = gv * gv;
 }
 
+// one shard [goff, goff + n) of a chain of nglob elements; halo = { xL, xR, dL, dR, .. } (device, the solver's)
+__global__ void rosen_eval_sharded(const double *x, const double *d, const double *d_alpha, double *g, double *tf, double *tgd,
+                                   double *tgg, size_t n, size_t goff, size_t nglob, const double *halo)
+{
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double a = *d_alpha;
+    const bool hl = goff + i > 0, hr = goff + i + 1 < nglob;
+    const double c = x[i] + a * d[i];
+    const double l = i > 0 ? x[i - 1] + a * d[i - 1] : (hl ? halo[0] + a * halo[2] : 0.0);
+    const double r = i + 1 < n ? x[i + 1] + a * d[i + 1] : (hr ? halo[1] + a * halo[3] : 0.0);
+    const double bl = c - l * l, bc = r - c * c, t2 = 1 - c;
+    const double from_left = hl ? 200.0 * bl : 0.0;
+    const double gv = hr ? from_left + (2.0 * (c - 1) - 400.0 * c * bc) : from_left;
+    g[i] = gv;
+    tf[i] = hr ? 100.0 * bc * bc + t2 * t2 : 0.0;
+    tgd[i] = gv * d[i];
+    tgg[i] = gv * gv;
+}
+
+struct ShardCtx {
+    double *tmp;        // 3 n_local doubles of device scratch
+    const double *halo; // lbfgsb200_device_halo(solver), filled in after create
+    size_t n_global;
+};
+
 __global__ void dense_eval(const double *A, const double *b, const double *x, const double *d, const double *d_alpha,
                            double *g, double *tf, double *tgd, double *tgg, size_t n)
 {
@@ -88,6 +118,27 @@ int cb_rosenbrock(const double *x, const double *d, const double *d_alpha, doubl
     rosen_eval<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, d, d_alpha, g_out, tmp, tmp + n, tmp + 2 * n, n);
     reduce3<<<1, 256, 0, st>>>(tmp, tmp + n, tmp + 2 * n, n, d_out3);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int cb_rosenbrock_sharded(const double *x, const double *d, const double *d_alpha, double *g_out, double *d_out3, size_t n,
+                          size_t global_offset, void *user, void *stream)
+{
+    const ShardCtx *c = (const ShardCtx *)user;
+    cudaStream_t st = (cudaStream_t)stream;
+    rosen_eval_sharded<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, d, d_alpha, g_out, c->tmp, c->tmp + n, c->tmp + 2 * n, n,
+                                                                    global_offset, c->n_global, c->halo);
+    reduce3<<<1, 256, 0, st>>>(c->tmp, c->tmp + n, c->tmp + 2 * n, n, d_out3);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int cb_rosenbrock_syncing(const double *x, const double *d, const double *d_alpha, double *g_out, double *d_out3, size_t n,
+                          size_t global_offset, void *user, void *stream)
+{
+    const int rc = cb_rosenbrock(x, d, d_alpha, g_out, d_out3, n, global_offset, user, stream);
+    // (during a capture this fails and invalidates the capture; the return value is deliberately ignored, as a
+    // careless user would)
+    cudaStreamSynchronize((cudaStream_t)stream);
+    return rc;
 }
 
 int cb_dense(const double *x, const double *d, const double *d_alpha, double *g_out, double *d_out3, size_t n,

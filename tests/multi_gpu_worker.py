@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--graph", type=int, default=0)
     ap.add_argument("--dir", dest="direction", default="two_loop")
+    ap.add_argument("--userlib", default="", help="--obj callback: tests/custom_objective.cu built as a shared library")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -51,12 +52,31 @@ def main():
     assert np.array_equal(pkg.x0_uniform(ln, lo, hi, offset=off), x0[off:off + ln])
     p = pkg.default_params(a.flavor, line_search=a.ls, m=a.m, max_iterations=a.iters, use_graph=a.graph,
                            direction=a.direction)
-    s = pkg.Solver(a.objective, a.n, p, comm=comm, trace_rows=a.iters)
+    if a.objective == "callback":
+        # a USER objective on a sharded solver: partial sums of this shard, neighbours' boundary values from the
+        # solver's device halo block; compared below with the built-in Rosenbrock on one GPU
+        import ctypes as C
+
+        class ShardCtx(C.Structure):
+            _fields_ = [("tmp", C.c_void_p), ("halo", C.c_void_p), ("n_global", C.c_size_t)]
+
+        user = C.CDLL(a.userlib)
+        tmp = pkg.DeviceBuffer(3 * ln)
+        ctx = ShardCtx(tmp.ptr, None, a.n)
+        s = pkg.Solver("callback", a.n, p, comm=comm, trace_rows=a.iters,
+                       callback=C.cast(user.cb_rosenbrock_sharded, C.c_void_p), user=C.addressof(ctx))
+        ctx.halo = s.device_halo()
+        a.objective = "rosenbrock"
+    else:
+        s = pkg.Solver(a.objective, a.n, p, comm=comm, trace_rows=a.iters)
     s.set_x0(np.ascontiguousarray(x0[off:off + ln]))
     s.iterate(a.iters)
     x_local = s.x()
     res, tr = s.result(), s.trace()
     s.destroy()
+    if a.userlib and res["graph"] != a.graph:
+        print("rank %d: graph mode %d, wanted %d" % (rank, res["graph"], a.graph), file=sys.stderr)
+        sys.exit(3)
     parts = [None] * world
     dist.all_gather_object(parts, (off, x_local))
     ok = True

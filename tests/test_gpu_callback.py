@@ -33,23 +33,50 @@ def _fn(lib, name):
     return C.cast(getattr(lib, name), C.c_void_p)
 
 
+@pytest.mark.parametrize("graph", [1, 0])
 @pytest.mark.parametrize("direction", ["two_loop", "compact"])
-def test_user_rosenbrock_matches_oracle(gpu, oracle, userlib, direction):
+def test_user_rosenbrock_matches_oracle(gpu, oracle, userlib, direction, graph):
+    """graph = 1 (the default): the callback is recorded into the solver's CUDA graph -- it runs on the host once per
+    call site, its kernels are replayed from the device for every evaluation."""
     for n, ls, flavor in ((10000, "wolfe", "par"), (4097, "backtracking", "seq"), (501, "interpolation", "par")):
         x0 = oracle.x0(n, -2, 2)
         K = 20
         xo, io, to = oracle.lbfgs("rosenbrock", x0, ls, flavor, 10, K, 1e-5, trace_rows=K)
         tmp = gpu.DeviceBuffer(3 * n)
-        p = gpu.default_params(flavor, line_search=ls, m=10, max_iterations=K, direction=direction)
+        p = gpu.default_params(flavor, line_search=ls, m=10, max_iterations=K, direction=direction, use_graph=graph)
         s = gpu.Solver("callback", n, p, trace_rows=K, callback=_fn(userlib, "cb_rosenbrock"), user=tmp.ptr)
         s.set_x0(x0)
+        s.iterate(7)          # resumable: several runs of the same recorded graph
         s.iterate(K + 1)
         x, r, tr = s.x(), s.result(), s.trace()
         s.destroy()
+        assert r["graph"] == graph
         assert r["iterations"] == io["iterations"] == K
         assert relvec(x, xo) <= 1e-10, (n, ls, relvec(x, xo))
         assert np.array_equal(tr[:, 4], to[:, 4]) and np.array_equal(tr[:, 5], to[:, 5])
         assert abs(r["f"] - io["f"]) <= 1e-10 * abs(io["f"])
+
+
+def test_callback_that_cannot_be_captured_falls_back_to_the_stepped_loop(gpu, oracle, userlib):
+    n, K = 3001, 15
+    x0 = oracle.x0(n, -2, 2)
+    xo, io, to = oracle.lbfgs("rosenbrock", x0, "wolfe", "par", 10, K, 1e-5, trace_rows=K)
+    tmp = gpu.DeviceBuffer(3 * n)
+    p = gpu.default_params("par", line_search="wolfe", m=10, max_iterations=K)  # use_graph = 1 by default
+    s = gpu.Solver("callback", n, p, trace_rows=K, callback=_fn(userlib, "cb_rosenbrock_syncing"), user=tmp.ptr)
+    s.set_x0(x0)
+    s.iterate(K)
+    x, r = s.x(), s.result()
+    s.destroy()
+    assert r["graph"] == 0 and r["iterations"] == K
+    assert relvec(x, xo) <= 1e-10
+    # and the library is still healthy: a capturable callback right after it runs in graph mode
+    s = gpu.Solver("callback", n, p, trace_rows=K, callback=_fn(userlib, "cb_rosenbrock"), user=tmp.ptr)
+    s.set_x0(x0)
+    s.iterate(K)
+    x2, r2 = s.x(), s.result()
+    s.destroy()
+    assert r2["graph"] == 1 and np.array_equal(x, x2)
 
 
 def test_dense_spd_known_answers_from_reference_fixtures(gpu, userlib):

@@ -51,6 +51,25 @@ def test_sharded_fused_compact_flow_equals_single_gpu(gpu, args, graph):
     assert out["ok"], out
 
 
+@pytest.mark.parametrize("graph", [0, 1])
+@pytest.mark.parametrize("args", [
+    ("--ls", "wolfe", "--flavor", "par", "--size", "100003", "--dir", "compact"),
+    ("--ls", "interpolation", "--flavor", "par", "--size", "20001", "--dir", "two_loop"),
+    ("--ls", "backtracking", "--flavor", "seq", "--size", "4097", "--dir", "compact", "--hist", "5"),
+])
+def test_user_objective_on_a_sharded_solver(gpu, tmp_path, args, graph):
+    """lbfgsb200_create_callback_sharded: a user-written chained Rosenbrock (tests/custom_objective.cu) evaluates its
+    shard with the neighbours' boundary values from lbfgsb200_device_halo(); host-stepped and recorded into the graph."""
+    ndev = gpu.lib().lbfgsb200_device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    out_lib = str(tmp_path / "libcustom_objective.so")
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-fmad=false", "-shared",
+                           "-Xcompiler", "-fPIC", os.path.join(ROOT, "tests", "custom_objective.cu"), "-o", out_lib])
+    out = _run(min(ndev, 2), "--obj", "callback", "--userlib", out_lib, *args, "--graph", str(graph))
+    assert out["ok"], out
+
+
 @pytest.mark.parametrize("args", [
     ("--obj", "rosenbrock", "--ls", "wolfe", "--flavor", "par", "--size", "100003", "--dir", "compact"),
     ("--obj", "rosenbrock", "--ls", "wolfe", "--flavor", "par", "--size", "65536", "--dir", "two_loop"),
