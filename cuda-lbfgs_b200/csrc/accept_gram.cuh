@@ -59,9 +59,11 @@ __device__ __forceinline__ void named_barrier_sync(int id, int threads)
 }
 
 // ---- accept + pass A ------------------------------------------------------------------------------
-//   warp 0        producer: <= 11 tensor-map TMA loads per tile (kept S / Y rows in <= 2 runs each, x, d, g_old, four
-//                 2-element halo boxes), one per lane, into the next free stage; completion is counted in bytes on
-//                 full[stage]
+//   warp 0        producer: <= 7 tensor-map TMA loads per tile (kept S / Y rows in <= 2 runs each; {x, g_old, d} as ONE
+//                 three-row box -- the arena keeps them adjacent in either parity of the iterate; two halo boxes of
+//                 2 columns x 4 rows), one per lane, into the next free stage; completion is counted in bytes on
+//                 full[stage].  The number of boxes matters: ~75 ns per UTMALDG and SM (11 boxes: 0.83 us per tile
+//                 whatever the history size -- the kernel was box-bound below h = 8)
 //   warps 1..4    accept (kAgGroups groups of 4 on alternating tiles; one group by default): wait full[stage]; one double2 item per lane: x + alpha d,
 //                 the three-point stencil by warp shuffles (warp-edge lanes read the tile, tile-edge lanes the halo
 //                 boxes), s, y, g_new, f; the x, d, g_old rows of the stage
@@ -78,6 +80,8 @@ constexpr int kAgGroupWarps = 4;                  // accept warps per group (4 x
 // accept groups working on alternating tiles (build-time tuning knob).  Measured on B200 at n = 1e8: 1 group 2.88-2.95 ms,
 // 2 groups 3.12-3.19 ms at m = 10; no difference at m = 3 -- the kernel is bound by the depth of the stage ring (a stage
 // is held for memory latency + accept + inner products), not by the accept rate, and extra warps only cost issue slots.
+// (With more than one group the stage count must be a multiple of the group count: a stage shared by two groups can be
+// tested one phase early by the group that runs ahead -- see k_combine_trial, which gives every group its own stages.)
 constexpr int kAgGroups = LB_AG_GROUPS;
 constexpr int kAgAcceptWarps = kAgGroupWarps * kAgGroups;
 constexpr int kAgGramWarps = 12;
@@ -90,8 +94,8 @@ constexpr int kAgMaxCW = 9; // columns per gram warp: at most ceil((2*50+1) / 12
 // re-computes the g row):
 //   rows 0 .. hk-1        kept S rows, window order          (TMA, <= 2 boxes)
 //   rows hk .. 2hk-1      kept Y rows                        (TMA, <= 2 boxes)
-//   rows 2hk, +1, +2      x, d, g_old tiles (TMA)  ->  s_new, y_new, g_new after the accept warps
-//   then 4 halo slots     x[i0-2..i0-1], x[i0+T..i0+T+1], d[i0-2..i0-1], d[i0+T..i0+T+1]   (TMA, 2-column boxes; a
+//   rows 2hk, +1, +2      {x, g_old, d} or {g_old, d, x} (TMA, one box)  ->  s_new, y_new, g_new after the accept warps
+//   then 2 halo slots     rows {x_a, g, w, x_b} x columns [i0-2, i0-1] and [i0+T, i0+T+1]   (TMA, 2-column boxes; a
 //                         plain global load of these elements would put a DRAM round trip under load -- longer than
 //                         a whole tile takes -- on the accept warps' critical path)
 constexpr int kHaloSlotDoubles = 16; // one 128-byte aligned slot per halo box (TMA destinations are 128-byte aligned)
@@ -102,9 +106,12 @@ __host__ __device__ inline size_t accept_gram_stage_doubles(int J, int T)
 
 template <class OBJ, int CW>
 __global__ void __launch_bounds__(kAgThreads, 1)
-k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ maps, int T, int NS, int init)
+k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ maps, int T, int NS, int init_and_boxes)
 {
     if (st->ctrl.done) return;
+    const int init = init_and_boxes & 1;
+    const bool halo_merged = (init_and_boxes & 2) != 0; // two halo boxes of 4 rows instead of four of 1 row
+    const bool xgd_merged = (init_and_boxes & 4) != 0;  // {x, g, d} as one 3-row box instead of three boxes
     extern __shared__ __align__(128) double tile[];
     __shared__ __align__(8) unsigned long long full[kMaxStages], ready[kMaxStages], empty[kMaxStages];
     __shared__ double fsum[kAgAcceptWarps];
@@ -136,15 +143,20 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
     for (int c = 0; c < CW; ++c) acc[c][0] = acc[c][1] = acc[c][2] = 0.0;
     double facc = 0.0;
     const int gw = warp - 1 - kAgAcceptWarps, cg = gw % NG, eg = gw / NG; // gram-warp coordinates (warp >= 9)
+    const bool x_is_a = st->x == st->arena0; // parity of the iterate: rows {x_a, g, w} or {g, w, x_b} hold {x, g, d}
 
     if (warp == 0) {
         // ---------------- producer ----------------
-        //   lane 0: S run A   1: Y run A   2: S run B   3: Y run B   4: x   5: d   6: g_old
-        //   lane 7: x left halo   8: x right halo   9: d left halo   10: d right halo   (2-column boxes)
+        //   lane 0: S run A   1: Y run A   2: S run B   3: Y run B
+        //   lane 4: {x, g_old, d} -- three consecutive arena rows in either parity of the iterate -- as ONE box, or
+        //           lanes 4, 5, 6: x, g_old, d as three boxes
+        //   lanes 7, 8: left / right halo as boxes of 2 columns x the 4 rows x_a, g, w, x_b, or
+        //           lanes 7 .. 10: x left, x right, d left, d right as four one-row boxes
+        //   (which of the two is faster depends on the history size: fewer boxes = less issue time, but the 4-row halo
+        //   boxes touch twice as many DRAM pages; the host picks per m, LBFGSB200_AG_BOXES overrides)
         const int ns = st->nslots;
         const int a0 = (st->base + ks) % ns;          // physical slot of the first kept pair
         const int ra = min(hk, ns - a0), rb = hk - ra; // the kept window is at most two runs of slots
-        const int row_x = (st->x == st->arena0) ? 0 : 1;
         const CUtensorMap *map = &maps->run[1];
         int row = 0;
         size_t off = 0; // destination inside the stage, in doubles
@@ -155,16 +167,23 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
         case 1: map = &maps->run[ra]; row = kArenaRowS + ns + a0; off = (size_t)hk * T; valid = ra > 0; break;
         case 2: map = &maps->run[rb]; row = kArenaRowS; off = (size_t)ra * T; valid = rb > 0; break;
         case 3: map = &maps->run[rb]; row = kArenaRowS + ns; off = (size_t)(hk + ra) * T; valid = rb > 0; break;
-        case 4: row = row_x; off = (size_t)(2 * hk) * T; break;
-        case 5: row = kArenaRowW; off = (size_t)(2 * hk + 1) * T; break;
-        case 6: row = kArenaRowG; off = (size_t)(2 * hk + 2) * T; break;
-        case 7: map = &maps->halo; row = row_x; off = (size_t)mrow * T; dcol = -2; break;
-        case 8: map = &maps->halo; row = row_x; off = (size_t)mrow * T + kHaloSlotDoubles; dcol = T; break;
-        case 9: map = &maps->halo; row = kArenaRowW; off = (size_t)mrow * T + 2 * kHaloSlotDoubles; dcol = -2; break;
-        case 10: map = &maps->halo; row = kArenaRowW; off = (size_t)mrow * T + 3 * kHaloSlotDoubles; dcol = T; break;
+        // {x, g, d}: rows {x_a, g, w} or {g, w, x_b} of the arena land in that order in stage rows 2hk .. 2hk+2
+        case 4:
+            if (xgd_merged) { map = &maps->run[3]; row = x_is_a ? kArenaRowXa : kArenaRowG; off = (size_t)(2 * hk) * T; }
+            else { row = x_is_a ? kArenaRowXa : kArenaRowXb; off = (size_t)(2 * hk + (x_is_a ? 0 : 2)) * T; }
+            break;
+        case 5: row = kArenaRowG; off = (size_t)(2 * hk + (x_is_a ? 1 : 0)) * T; valid = !xgd_merged; break;
+        case 6: row = kArenaRowW; off = (size_t)(2 * hk + (x_is_a ? 2 : 1)) * T; valid = !xgd_merged; break;
+        // halo: merged = [row x_a, g, w, x_b][2 columns] left / right; else one slot each: x left, x right, d left, d right
+        case 7: map = halo_merged ? &maps->halo : &maps->halo1; row = halo_merged ? 0 : (x_is_a ? kArenaRowXa : kArenaRowXb);
+                off = (size_t)mrow * T; dcol = -2; break;
+        case 8: map = halo_merged ? &maps->halo : &maps->halo1; row = halo_merged ? 0 : (x_is_a ? kArenaRowXa : kArenaRowXb);
+                off = (size_t)mrow * T + kHaloSlotDoubles; dcol = T; break;
+        case 9: map = &maps->halo1; row = kArenaRowW; off = (size_t)mrow * T + 2 * kHaloSlotDoubles; dcol = -2; valid = !halo_merged; break;
+        case 10: map = &maps->halo1; row = kArenaRowW; off = (size_t)mrow * T + 3 * kHaloSlotDoubles; dcol = T; valid = !halo_merged; break;
         default: valid = false; break;
         }
-        const unsigned bytes = (unsigned)(((size_t)nrow * T + 8) * sizeof(double));
+        const unsigned bytes = (unsigned)(((size_t)nrow * T + (halo_merged ? 2 * 8 : 4 * 2)) * sizeof(double));
         PipeState ps = {0, 1u}; // the producer waits for the PREVIOUS use of a stage to be released
         long long col = (long long)blockIdx.x * T;
         for (long long k = 0; k < my_tiles; ++k, col += tile_stride, ps.advance(1, NS)) {
@@ -188,13 +207,19 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
         double *__restrict__ y_out = st->Y + sp;
         const int e = aw * 32 + lane;   // double2 item of this lane within the tile
         const bool act = e < T2;
+        // where the elements just outside the tile are, relative to the halo area of the stage
+        const int hrx = 2 * (x_is_a ? kArenaRowXa : kArenaRowXb), hrd = 2 * kArenaRowW;
+        const int hxl = halo_merged ? hrx + 1 : 1, hdl = halo_merged ? hrd + 1 : 2 * kHaloSlotDoubles + 1;
+        const int hxr = halo_merged ? kHaloSlotDoubles + hrx : kHaloSlotDoubles, hdr = halo_merged ? kHaloSlotDoubles + hrd : 3 * kHaloSlotDoubles;
         long long col = ((long long)blockIdx.x + grp * (long long)gridDim.x) * T; // first element of the group's first tile
         PipeState ps = pipe_at(grp, NS);
         for (long long k = grp; k < my_tiles; k += kAgGroups, col += kAgGroups * tile_stride, ps.advance(kAgGroups, NS)) {
             mbar_wait(&full[ps.stage], ps.phase);
             double *cur = tile + ps.stage * stage_doubles;
-            double *in_x = cur + (size_t)(2 * hk) * T, *in_d = in_x + T, *in_g = in_d + T;
-            const double *halo = cur + (size_t)mrow * T; // x[col-2..col-1], x[col+T..], d[col-2..col-1], d[col+T..]
+            double *out_s = cur + (size_t)(2 * hk) * T, *out_y = out_s + T, *out_g = out_y + T; // the three new rows, in place
+            const double *in_x = x_is_a ? out_s : out_g, *in_g = x_is_a ? out_y : out_s, *in_d = x_is_a ? out_g : out_y;
+            // halo boxes: [row x_a, g, w, x_b][2 columns]; left = elements col-2, col-1, right = col+T, col+T+1
+            const double *halo = cur + (size_t)mrow * T;
             const long long ge = col + 2 * (long long)e; // first element of the item
             double2 xc = make_double2(0.0, 0.0), dc = xc, go = xc;
             if (act) {
@@ -213,13 +238,13 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
                         const int tl = 2 * e - 1; // tile coordinate of the left neighbour
                         if (ge == 0) l = xtL;
                         else if (tl >= 0) l = in_x[tl] + alpha * in_d[tl];
-                        else l = halo[1] + alpha * halo[2 * kHaloSlotDoubles + 1];
+                        else l = halo[hxl] + alpha * halo[hdl];
                     }
                     if (ge + 2 >= n) r = xtR;
                     else if (lane == 31) {
                         const int tr = 2 * e + 2;
                         if (tr < T) r = in_x[tr] + alpha * in_d[tr];
-                        else r = halo[kHaloSlotDoubles] + alpha * halo[3 * kHaloSlotDoubles];
+                        else r = halo[hxr] + alpha * halo[hdr];
                     }
                 }
             }
@@ -257,9 +282,9 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
                         y_out[ge] = a1.x;
                     }
                 }
-                reinterpret_cast<double2 *>(in_x)[e] = a0; // s_new
-                reinterpret_cast<double2 *>(in_d)[e] = a1; // y_new
-                reinterpret_cast<double2 *>(in_g)[e] = a2; // g_new
+                reinterpret_cast<double2 *>(out_s)[e] = a0; // s_new
+                reinterpret_cast<double2 *>(out_y)[e] = a1; // y_new
+                reinterpret_cast<double2 *>(out_g)[e] = a2; // g_new
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&ready[ps.stage]); // release: the three new rows of this stage are in place
@@ -327,7 +352,8 @@ k_accept_gram(const DevState *__restrict__ st, const ArenaMaps *__restrict__ map
 }
 
 // ---- pass B + first trial ------------------------------------------------------------------------
-// Warp 0 issues <= 6 tensor-map TMA loads per tile (S and Y in <= 2 runs each, g, x), one per lane; two groups of 4
+// Warp 0 issues <= 6 tensor-map TMA loads per tile (S and Y in <= 2 runs each; {x, g} as one box when the iterate is
+// x_a, else g and x_b), one per lane; two groups of 4
 // consumer warps take alternating tiles, one double2 item per lane: the fma chain over the 2h+1 columns out of shared
 // memory (window-column order: the chain k_combine uses, so d has the same bits), the store of d, the trial point, the
 // stencil by warp shuffles, warp-edge values going through a small shared-memory exchange and ONE named barrier per
@@ -345,6 +371,8 @@ constexpr int kCtThreads = 32 * (kCtWarps + 1);
 constexpr int kCtHaloItems = 4; // default double2 items of overlap on each side of a tile
 
 __host__ __device__ inline size_t combine_trial_stage_doubles(int m, int T) { return (size_t)(2 * m + 2) * T; }
+// stages of the ring that belong to consumer group g (physical stages g, g + kCtGroups, ... < NS)
+__host__ __device__ inline int ct_group_stages(int NS, int g) { return (NS - g + kCtGroups - 1) / kCtGroups; }
 
 template <class OBJ>
 __global__ void __launch_bounds__(kCtThreads, 1)
@@ -376,13 +404,14 @@ k_combine_trial(const DevState *__restrict__ st, const ArenaMaps *__restrict__ m
     const long long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const long long item_stride = (long long)gridDim.x * own2; // items between consecutive tiles of this CTA
     double a_gd = 0.0, a_f = 0.0, a_gdt = 0.0;
+    const bool x_is_a = st->x == st->arena0; // rows 2hh, 2hh+1 of a stage hold [x, g] (one box) or [g, x] (two boxes)
 
     if (warp == 0) {
-        // producer: lane 0: S run A   1: S run B   2: Y run A   3: Y run B   4: g   5: x   (rows in window-column order)
+        // producer: lane 0: S run A   1: S run B   2: Y run A   3: Y run B (rows in window-column order), then g and x:
+        // adjacent arena rows {x_a, g} when the iterate is x_a -- ONE box, landing as [x, g] -- else lane 4: g, lane 5: x_b
         const int ns = st->nslots, b0 = st->base;
         const int ra = steep ? 0 : min(h, ns - b0), rb = steep ? 0 : h - ra;
         const int hh = steep ? 0 : h;
-        const int row_x = (st->x == st->arena0) ? 0 : 1;
         const CUtensorMap *map = &maps->run[1];
         int row = 0;
         size_t off = 0;
@@ -392,20 +421,38 @@ k_combine_trial(const DevState *__restrict__ st, const ArenaMaps *__restrict__ m
         case 1: map = &maps->run[rb]; row = kArenaRowS; off = (size_t)ra * T; valid = rb > 0; break;
         case 2: map = &maps->run[ra]; row = kArenaRowS + ns + b0; off = (size_t)hh * T; valid = ra > 0; break;
         case 3: map = &maps->run[rb]; row = kArenaRowS + ns; off = (size_t)(hh + ra) * T; valid = rb > 0; break;
-        case 4: row = kArenaRowG; off = (size_t)(2 * hh) * T; break;
-        case 5: row = row_x; off = (size_t)(2 * hh + 1) * T; break;
+        case 4: map = &maps->run[x_is_a ? 2 : 1]; row = x_is_a ? kArenaRowXa : kArenaRowG; off = (size_t)(2 * hh) * T; break;
+        case 5: row = kArenaRowXb; off = (size_t)(2 * hh + 1) * T; valid = !x_is_a; break;
         default: valid = false; break;
         }
         const unsigned bytes = (unsigned)((size_t)(2 * hh + 2) * T * sizeof(double));
-        PipeState ps = {0, 1u};
+        // Every consumer group owns its OWN stages (group g: physical stages g, g + G, ...; sub-ring of ct_group_stages
+        // entries): a stage is then always filled for, and released by, the same group, in that group's tile order.
+        // With one shared ring and an odd stage count the two groups would alternate on a stage, and a group that runs
+        // ahead could test a stage's `full` barrier one phase early -- the parity of the phase before last looks
+        // "completed" -- and consume a tile that is still in flight (TMA loads complete out of order).
+        PipeState ps[kCtGroups];
+#pragma unroll
+        for (int g = 0; g < kCtGroups; ++g) ps[g] = PipeState{0, 1u}; // (a fresh barrier passes the wait on parity 1)
         long long first = (long long)blockIdx.x * own2 - halo2; // first item of the tile (negative for the very first: zero-filled)
-        for (long long k = 0; k < my_tiles; ++k, first += item_stride, ps.advance(1, NS)) {
+        int g = 0;
+        for (long long k = 0; k < my_tiles; ++k, first += item_stride) {
+            int stage = 0;
+            unsigned phase = 0;
+#pragma unroll
+            for (int q = 0; q < kCtGroups; ++q) // (static indexing: the states stay in registers)
+                if (q == g) {
+                    stage = q + kCtGroups * ps[q].stage;
+                    phase = ps[q].phase;
+                    ps[q].advance(1, ct_group_stages(NS, q));
+                }
             if (lane == 0) {
-                if (k >= NS) mbar_wait(&empty[ps.stage], ps.phase);
-                mbar_expect_tx(&full[ps.stage], bytes);
+                mbar_wait(&empty[stage], phase);
+                mbar_expect_tx(&full[stage], bytes);
             }
             __syncwarp();
-            if (valid) tma_load_2d(tile + ps.stage * stage_doubles + off, map, (int)(2 * first), row, &full[ps.stage]);
+            if (valid) tma_load_2d(tile + stage * stage_doubles + off, map, (int)(2 * first), row, &full[stage]);
+            if (++g == kCtGroups) g = 0;
         }
     } else {
         const int grp = (warp - 1) / kCtGroupWarps, cwp = (warp - 1) % kCtGroupWarps;
@@ -417,24 +464,29 @@ k_combine_trial(const DevState *__restrict__ st, const ArenaMaps *__restrict__ m
         const double xtL = st->xL + alpha * st->dL, xtR = st->xR + alpha * st->dR;
         const long long goff = st->goff, nglob = st->nglob;
         double *__restrict__ w = st->w;
-        PipeState ps = pipe_at(grp, NS);
+        PipeState ps = {0, 0u}; // this group's sub-ring: physical stage = grp + kCtGroups * ps.stage
+        const int my_stages = ct_group_stages(NS, grp);
         long long first = ((long long)blockIdx.x + grp * (long long)gridDim.x) * own2 - halo2;
         int buf = 0;
-        for (long long k = grp; k < my_tiles; k += kCtGroups, first += kCtGroups * item_stride, ps.advance(kCtGroups, NS), buf ^= 1) {
-            mbar_wait(&full[ps.stage], ps.phase);
-            const double2 *cur2 = reinterpret_cast<const double2 *>(tile + ps.stage * stage_doubles);
+        for (long long k = grp; k < my_tiles; k += kCtGroups, first += kCtGroups * item_stride, ps.advance(1, my_stages), buf ^= 1) {
+            const int stage = grp + kCtGroups * ps.stage;
+            mbar_wait(&full[stage], ps.phase);
+            const double2 *cur2 = reinterpret_cast<const double2 *>(tile + stage * stage_doubles);
             const long long i = first + e; // global item index (may be < 0 or beyond the vector: zeros)
             double2 s = make_double2(0.0, 0.0), gv = s, xv = s;
             if (in_tile) {
 #pragma unroll 4
-                for (int j = 0; j < J; ++j) {
+                for (int j = 0; j < J - 1; ++j) { // the S and Y columns, window-column order
                     const double c = coef[j];
                     const double2 v = cur2[(size_t)j * T2 + e];
                     s.x = fma(c, v.x, s.x);
                     s.y = fma(c, v.y, s.y);
-                    if (j == J - 1) gv = v;
                 }
-                xv = cur2[(size_t)(2 * hh + 1) * T2 + e];
+                gv = cur2[(size_t)(2 * hh + (x_is_a ? 1 : 0)) * T2 + e]; // last column: g
+                xv = cur2[(size_t)(2 * hh + (x_is_a ? 0 : 1)) * T2 + e];
+                const double c = coef[J - 1];
+                s.x = fma(c, gv.x, s.x);
+                s.y = fma(c, gv.y, s.y);
             }
             s.x = -s.x;
             s.y = -s.y;
@@ -470,7 +522,7 @@ k_combine_trial(const DevState *__restrict__ st, const ArenaMaps *__restrict__ m
                 a_gdt += q0 * s.x + q1 * s.y;
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[ps.stage]);
+            if (lane == 0) mbar_arrive(&empty[stage]);
         }
     }
     __syncthreads();

@@ -165,7 +165,7 @@ k_gram(const DevState *__restrict__ st, int T, int NS, int G)
 // copy instructions (the LDGSTS version spends ~40% of its MIO slots issuing copies), shared memory is
 // read back with 128-bit loads, and the consumer warps are split into NG column groups x 16/NG
 // element groups so that each row value is re-read NG times.
-constexpr int kMaxStages = 8; // upper bound of the shared-memory ring depth (the kernels take the actual count NS <= kMaxStages)
+constexpr int kMaxStages = 8;  // upper bound of the shared-memory ring depth (the kernels take the actual count NS <= kMaxStages)
 constexpr int kRegRecursionH = 13; // histories up to this size run the coefficient recursion out of registers (J <= 27 lanes)
 constexpr int kGramStages = 4; // ring depth of the stand-alone pass A
 
@@ -215,16 +215,22 @@ constexpr int kWsThreads = 32 * (kWsConsumerWarps + 1);
 // (the box shape is part of the map) and live in global memory.  Out-of-range columns of the last
 // tile are zero-filled by the TMA unit, and the transaction count is always the full box.
 // Producer / consumer structure, tile layout and arithmetic are those of k_gram_tma.
-// Tensor maps over the WHOLE arena, a row-major [4 + 2 nslots][stride] FP64 tensor (rows: x, x_alt, g, w,
-// S slots, Y slots): run[r] = box of T columns x r rows (r consecutive ring slots, or one of x / d / g with
-// r = 1), halo = box of 2 columns x 1 row (the element just outside a tile, accept_gram.cuh).  Out-of-range
-// columns (negative or >= stride) are zero-filled by the TMA unit and still count for the full box in the
-// transaction bytes.  Built on the host per solver (cuTensorMapEncodeTiled) and kept in global memory.
+// Tensor maps over the WHOLE arena, a row-major [4 + 2 nslots][stride] FP64 tensor (rows: x_a, g, w, x_b,
+// S slots, Y slots): run[r] = box of T columns x r rows (r consecutive ring slots; r = 3: {x_a, g, w} or {g, w, x_b};
+// r = 2: {x_a, g}), halo = box of 2 columns x 4 rows (the elements of x_a, g, w, x_b just outside a tile,
+// accept_gram.cuh).  Out-of-range columns (negative or >= stride) are zero-filled by the TMA unit and still count for
+// the full box in the transaction bytes.  Built on the host per solver (cuTensorMapEncodeTiled), kept in global memory.
+//
+// Row order: the iterate ping-pongs between x_a and x_b (the accept step writes x_new to the one that is not x), with
+// g and w (= d) between them, so that {x, g, d} are THREE CONSECUTIVE ROWS in either parity -- one TMA box instead
+// of three.  The fused kernels are bound by the number of boxes per tile at small histories (~75 ns per UTMALDG
+// and SM, measured: k_accept_gram took 0.83 us per tile with 11 boxes whatever the history size).
 struct ArenaMaps {
     CUtensorMap run[kMaxSlots + 1];
-    CUtensorMap halo;
+    CUtensorMap halo;  // 2 columns x 4 rows
+    CUtensorMap halo1; // 2 columns x 1 row
 };
-constexpr int kArenaRowX = 0, kArenaRowG = 2, kArenaRowW = 3, kArenaRowS = 4;
+constexpr int kArenaRowXa = 0, kArenaRowG = 1, kArenaRowW = 2, kArenaRowXb = 3, kArenaRowS = 4;
 
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1,
                                             unsigned long long *bar)
@@ -366,6 +372,23 @@ __global__ void __launch_bounds__(kScalarThreads) k_gram_finalize(DevState *st, 
     }
 }
 
+// ---- diagnostic timeline (LBFGSB200_TIMELINE): rows of (op, t_in, %globaltimer now); ops >= 100 are sub-marks ----
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void tl_mark(DevState *st, int op, unsigned long long t_in)
+{
+    if (st->tl && threadIdx.x == 0 && st->tl_n < st->tl_cap) {
+        unsigned long long *row = st->tl + 3 * (size_t)st->tl_n++;
+        row[0] = (unsigned long long)(long long)op;
+        row[1] = t_in;
+        row[2] = op >= 100 ? (unsigned long long)clock64() : global_ns(); // sub-marks: SM cycles next to the ns in row[1]
+    }
+}
+
 // Gram bookkeeping + the two loops of seq/lbfgs.cpp:93-143 on coefficients.  Called by every thread of the scalar
 // kernel's CTA.
 // rows: the finalised 3 x J inner products of pass A (already summed over ranks on multi-GPU).
@@ -408,6 +431,7 @@ __device__ void compact_recursion(DevState *st, const double *rows, double *Gs, 
         if (from_rows) G[bi[a] * NB + bi[b]] = v;
     }
     __syncthreads();
+    tl_mark(st, 104, global_ns()); // (window Gram matrix staged)
     if (!run || threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
     // Everything the 2h dependent steps touch lives in STATIC shared memory and is addressed directly, the window Gram
@@ -519,6 +543,7 @@ __device__ void compact_recursion(DevState *st, const double *rows, double *Gs, 
         if (lane == 0) delta_s[jg] = 1.0 * gamma;                                   // coefficient of g
         __syncwarp();
     }
+    tl_mark(st, 105, global_ns()); // (both loops done)
     for (int i = lane; i < J; i += 32) st->delta[i] = delta_s[i];
     for (int p = lane; p < h; p += 32) st->alpha[p] = als[p];
     __syncwarp();

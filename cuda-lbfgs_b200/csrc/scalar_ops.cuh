@@ -122,12 +122,6 @@ __device__ __forceinline__ unsigned long long *mail_counter(double *base)
 {
     return reinterpret_cast<unsigned long long *>(base) + (size_t)2 * kMailRanks * (size_t)(2 * kMailWidth);
 }
-__device__ __forceinline__ unsigned long long global_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 
 struct P2pTicket {
     int par;
@@ -435,15 +429,6 @@ __device__ void scalar_logic(DevState *st, int op, int p, const double *r)
     }
 }
 
-__device__ __forceinline__ void tl_mark(DevState *st, int op, unsigned long long t_in)
-{
-    if (st->tl && threadIdx.x == 0 && st->tl_n < st->tl_cap) {
-        unsigned long long *row = st->tl + 3 * (size_t)st->tl_n++;
-        row[0] = (unsigned long long)(long long)op;
-        row[1] = t_in;
-        row[2] = global_ns();
-    }
-}
 
 // device-side control flow of graph mode: the iteration loop and the trial loop are WHILE nodes, the stand-alone
 // pass A of the fused flow an IF node (thread 0 only; legal only inside the graph, hence the use_graph gate)

@@ -175,6 +175,7 @@ struct lbfgsb200_solver {
     lbfgsb200_fg_device_fn cb = nullptr;     // user device objective (lbfgsb200_create_callback)
     void *cb_user = nullptr;
     double *cb_buf = nullptr;                // g_trial [stride] + {f, g.d, g.g} + a device zero
+    int ag_boxes = 3;                        // k_accept_gram box layout: bit 0 merged halo boxes, bit 1 merged {x, g, d} box
     bool cb_graph_failed = false;            // the callback could not be stream-captured: host-stepped loop instead
     accept_kernel_t accept_kernel = nullptr;
 
@@ -249,6 +250,22 @@ struct NvtxRange {
 // scalar step: on one GPU the scalar kernel sums the partials itself; on several the local sums
 // and halo values are packed, exchanged (NVLink mailboxes inside the scalar kernel, or one small NCCL
 // all-gather) and summed in rank order.
+// LBFGSB200_DEBUG_SYNC=1 (host-stepped loop only): synchronise after every launch and name the kernel that failed
+static int debug_sync(lbfgsb200_solver *s, const char *what, int op = -100)
+{
+    static const bool on = getenv("LBFGSB200_DEBUG_SYNC") != nullptr;
+    if (!on) return 0;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s->stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return 0;
+    const cudaError_t e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) {
+        set_error("%s (op %d) failed: %s [k=%lld]", what, op, cudaGetErrorString(e), (long long)s->k_host);
+        fprintf(stderr, "lbfgsb200: %s\n", lbfgsb200_last_error());
+        return LBFGSB200_ERR_CUDA;
+    }
+    return 0;
+}
+
 static int scalar_step(lbfgsb200_solver *s, int op, int p, int pack_kind, int nparts_override = -1)
 {
     const int nparts = nparts_override >= 0 ? nparts_override
@@ -270,7 +287,7 @@ static int scalar_step(lbfgsb200_solver *s, int op, int p, int pack_kind, int np
         k_scalar<<<1, kScalarThreads, 0, s->stream>>>(s->d_st, op, p, 0, PACK_NONE, nparts);
         s->launches += 1;
     }
-    return 0;
+    return debug_sync(s, "k_scalar", op);
 }
 
 // the stand-alone pass A (old compact flow; fused flow: only after a rejected pair with a full ring)
@@ -309,7 +326,7 @@ static int rows_step(lbfgsb200_solver *s, int op, int nparts)
     }
     k_scalar<<<1, kScalarThreads, dyn, s->stream>>>(s->d_st, op, 0, p2p ? 2 : (multi ? 1 : 0), PACK_NONE, nparts);
     s->launches += 1;
-    return 0;
+    return debug_sync(s, "k_scalar(rows)", op);
 }
 
 // search direction: seq/lbfgs.cpp:86-153 (explicit two-loop recursion, or the UNFUSED compact form, which user
@@ -422,6 +439,7 @@ static int run_stepped(lbfgsb200_solver *s, int64_t iterations)
 static int callback_eval(lbfgsb200_solver *s, const double *d_alpha, double *d_out3)
 {
     if (s->cb(s->arena, s->h_snapshot.w, d_alpha, s->cb_buf, d_out3, s->n_local, s->offset, s->cb_user, s->stream)) {
+        if (getenv("LBFGSB200_VERBOSE")) fprintf(stderr, "lbfgsb200: the objective callback returned non-zero (last CUDA error: %s)\n", cudaGetErrorName(cudaPeekAtLastError()));
         set_error("the objective callback failed");
         return LBFGSB200_ERR_INVALID;
     }
@@ -476,8 +494,9 @@ static int run_stepped_callback(lbfgsb200_solver *s, int64_t iterations)
 static void launch_accept_gram(lbfgsb200_solver *s, int init)
 {
     ClassTimer t(s, KC_GRAM);
-    s->ag_kernel<<<s->grid_ag, kAgThreads, s->ag_smem, s->stream>>>(s->d_st, s->arena_maps, s->gram_T, s->gram_NS, init);
+    s->ag_kernel<<<s->grid_ag, kAgThreads, s->ag_smem, s->stream>>>(s->d_st, s->arena_maps, s->gram_T, s->gram_NS, init | (s->ag_boxes << 1));
     s->launches += 1;
+    debug_sync(s, "k_accept_gram", init);
 }
 
 static int fused_fix_segment(lbfgsb200_solver *s)
@@ -492,6 +511,7 @@ static int fused_direction_segment(lbfgsb200_solver *s)
         ClassTimer t(s, KC_COMBINE);
         s->ct_kernel<<<s->grid_combine, kCtThreads, s->ct_smem, s->stream>>>(s->d_st, s->arena_maps_ct, s->ct_T, s->ct_NS, s->ct_halo);
         s->launches += 1;
+        debug_sync(s, "k_combine_trial");
     }
     return scalar_step(s, OP_F_DIR, 0, PACK_NONE);
 }
@@ -671,8 +691,8 @@ static bool wants_graph(const lbfgsb200_solver *s)
 }
 
 // Can the user's callback be recorded?  One evaluation is captured into a throw-away graph: the capture must
-// survive (a callback that synchronises, allocates with cudaMalloc or touches the legacy stream invalidates it) and
-// may only have produced what a conditional-node body accepts -- kernel, memcpy, memset and empty nodes (no
+// survive, no CUDA call of the callback may have failed (synchronising, cudaMalloc, the legacy stream: all illegal
+// while capturing), and it may only have produced what a conditional-node body accepts -- kernel, memcpy, memset and empty nodes (no
 // stream-ordered allocations, host functions or event nodes).
 static bool callback_is_capturable(lbfgsb200_solver *s)
 {
@@ -682,11 +702,15 @@ static bool callback_is_capturable(lbfgsb200_solver *s)
         return false;
     }
     s->stream = s->capture_stream;
+    cudaGetLastError();
     const int rc = callback_eval(s, &s->d_st->ls.alpha, s->partials);
+    // a CUDA call of the callback that is illegal during capture (a synchronisation, say) may fail without
+    // invalidating the capture: the error it left behind is the tell
+    const cudaError_t pending = cudaGetLastError();
     s->stream = run_stream;
     cudaGraph_t g = nullptr;
     const cudaError_t e = cudaStreamEndCapture(s->capture_stream, &g);
-    bool ok = rc == 0 && e == cudaSuccess && g != nullptr;
+    bool ok = rc == 0 && pending == cudaSuccess && e == cudaSuccess && g != nullptr;
     if (ok) {
         size_t count = 0;
         ok = cudaGraphGetNodes(g, nullptr, &count) == cudaSuccess && count > 0;
@@ -700,7 +724,10 @@ static bool callback_is_capturable(lbfgsb200_solver *s)
         }
     }
     if (g) cudaGraphDestroy(g);
-    cudaGetLastError();
+    const cudaError_t left = cudaGetLastError();
+    if (getenv("LBFGSB200_VERBOSE"))
+        fprintf(stderr, "lbfgsb200: callback probe capture: rc=%d pending=%s end=%s graph=%p left=%s -> %s\n", rc, cudaGetErrorName(pending),
+                cudaGetErrorName(e), (void *)g, cudaGetErrorName(left), ok ? "capturable" : "not capturable");
     return ok;
 }
 
@@ -882,8 +909,8 @@ static int build_arena_maps(lbfgsb200_solver *s, ArenaMaps *dev_dst, int box_T, 
         return r == CUDA_SUCCESS;
     };
     bool ok = true;
-    for (int r = 1; r <= s->nslots && ok; ++r) ok = make(&host->run[r], box_T, r);
-    ok = ok && make(&host->halo, 2, 1);
+    for (int r = 1; r <= (s->nslots > 3 ? s->nslots : 3) && ok; ++r) ok = make(&host->run[r], box_T, r);
+    ok = ok && make(&host->halo, 2, 4) && make(&host->halo1, 2, 1);
     if (!ok) return LBFGSB200_ERR_CUDA;
     // (the host copy lives in the solver: the upload is stream-ordered)
     CUDA_TRY(cudaMemcpyAsync(dev_dst, host, sizeof(ArenaMaps), cudaMemcpyHostToDevice, s->stream));
@@ -1005,7 +1032,7 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
             const char *eb = getenv("LBFGSB200_GRAM_TMA_KB");
             const size_t budget = (size_t)(eb ? atoi(eb) : 216) * 1024;
             budget_bytes = budget;
-            auto pick_tile = [&](size_t rows, const char *envname, int *T_out, int *NS_out) {
+            auto pick_tile = [&](size_t rows, size_t budget, const char *envname, int *T_out, int *NS_out) {
                 // measured on B200 (benchmarks/tile_sweep.sh, n = 1e8): 2 stages of 256 beat 3 of 192 beat 4 of 128
                 // (m = 20: 86.6 / 83.3 / 79.8 it/s), so the widest tile with >= 2 stages wins
                 static const int widths[] = {256, 192, 128, 64};
@@ -1022,8 +1049,15 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
                 *T_out = T;
                 *NS_out = NS;
             };
-            pick_tile((size_t)J, "LBFGSB200_AG_TILE", &s->gram_T, &s->gram_NS);
-            pick_tile((size_t)J + 1, "LBFGSB200_CT_TILE", &s->ct_T, &s->ct_NS); // one row more: x
+            pick_tile((size_t)J, budget, "LBFGSB200_AG_TILE", &s->gram_T, &s->gram_NS);
+            // k_accept_gram box layout (accept_gram.cuh).  Measured on B200 at n = 1e8 (boxes = 0 / 1 / 2 / 3):
+            //   m = 5 : 230.0 / 234.6 / 235.8 / 242.4 it/s   (box-issue-bound: fewer boxes win)
+            //   m = 10: 167.0 / 164.9 / 164.9 / 162.6 it/s   (DRAM-bound: independent one-row boxes win)
+            s->ag_boxes = params->m <= 7 ? 3 : 0;
+            if (const char *e = getenv("LBFGSB200_AG_BOXES")) s->ag_boxes = atoi(e) & 3;
+            if (kAgGroups > 1 && s->gram_NS >= 2 * kAgGroups) s->gram_NS -= s->gram_NS % kAgGroups; // (accept_gram.cuh: groups must not share a stage)
+            // one row more (x), and ~9 KB of the CTA's shared memory are static (the boundary exchange of its two groups)
+            pick_tile((size_t)J + 1, budget - 8192, "LBFGSB200_CT_TILE", &s->ct_T, &s->ct_NS);
             if (const char *e = getenv("LBFGSB200_CT_HALO")) s->ct_halo = atoi(e) >= 1 && 2 * atoi(e) < s->ct_T / 4 ? atoi(e) : kCtHaloItems;
             s->ag_smem = (size_t)s->gram_NS * accept_gram_stage_doubles(J, s->gram_T) * sizeof(double);
             s->ct_smem = (size_t)s->ct_NS * combine_trial_stage_doubles(params->m, s->ct_T) * sizeof(double);
@@ -1136,7 +1170,7 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     // HBM pass over (2m+6) vectors on every create().
     {
         const size_t pad = s->stride - s->n_local;
-        CREATE_TRY(cudaMemsetAsync(s->arena + 3 * s->stride, 0, s->stride * sizeof(double), s->stream));
+        CREATE_TRY(cudaMemsetAsync(s->arena + kArenaRowW * s->stride, 0, s->stride * sizeof(double), s->stream));
         if (pad) // one strided memset for the pad of every row
             CREATE_TRY(cudaMemset2DAsync(s->arena + s->n_local, s->stride * sizeof(double), 0, pad * sizeof(double), nvecs, s->stream));
     }
@@ -1200,7 +1234,7 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
             s_optin[s->device] = optin;
             opted[s->device] = true;
         }
-        const size_t need = (s->fused ? (s->ag_smem > s->ct_smem ? s->ag_smem : s->ct_smem) : s->gram_smem) + 4096;
+        const size_t need = (s->fused ? (s->ag_smem + 1024 > s->ct_smem + 10240 ? s->ag_smem + 1024 : s->ct_smem + 10240) : s->gram_smem + 1024) + 1024;
         if ((size_t)s_optin[s->device] < need) {
             set_error("pass A needs %zu bytes of shared memory, the device offers %d", need, s_optin[s->device]);
             lbfgsb200_destroy(s);
@@ -1229,10 +1263,10 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     st.grid_accept = s->grid_accept;
     st.arena0 = s->arena;
     st.x = s->arena;
-    st.x_alt = s->arena + s->stride;
-    st.g = s->arena + 2 * s->stride;
-    st.w = s->arena + 3 * s->stride;
-    st.S = s->arena + 4 * s->stride;
+    st.x_alt = s->arena + kArenaRowXb * s->stride;
+    st.g = s->arena + kArenaRowG * s->stride;
+    st.w = s->arena + kArenaRowW * s->stride;
+    st.S = s->arena + kArenaRowS * s->stride;
     st.Y = st.S + (size_t)s->nslots * s->stride;
     st.stride = (long long)s->stride;
     st.fused = s->fused ? 1 : 0;
@@ -1441,8 +1475,8 @@ int lbfgsb200_checkpoint_load(lbfgsb200_solver_t *s, const char *path)
     // scalars come from the file; every pointer and handle from this solver
     const DevState &cur = s->h_snapshot;
     st.arena0 = s->arena;
-    st.x = h.x_is_alt ? s->arena + s->stride : s->arena;
-    st.x_alt = s->cb ? st.x : (h.x_is_alt ? s->arena : s->arena + s->stride);
+    st.x = h.x_is_alt ? s->arena + kArenaRowXb * s->stride : s->arena;
+    st.x_alt = s->cb ? st.x : (h.x_is_alt ? s->arena : s->arena + kArenaRowXb * s->stride);
     st.g = cur.g; st.w = cur.w; st.S = cur.S; st.Y = cur.Y;
     st.partials = cur.partials; st.send = cur.send; st.recv = cur.recv; st.trace = cur.trace;
     st.gram = cur.gram; st.gram_rows = cur.gram_rows; st.gram_recv = cur.gram_recv; st.delta = cur.delta;
@@ -1554,7 +1588,7 @@ int lbfgsb200_set_x0(lbfgsb200_solver_t *s, const double *x0_local)
     // restore the pristine state (ring empty, pointers un-swapped), then evaluate f(x0), g(x0)
     DevState &st = s->h_snapshot;
     st.x = s->arena;
-    st.x_alt = s->cb ? s->arena : s->arena + s->stride; // user objectives: x is updated in place
+    st.x_alt = s->cb ? s->arena : s->arena + kArenaRowXb * s->stride; // user objectives: x is updated in place
     st.base = 0;
     st.h = 0;
     st.k = 0;

@@ -8,8 +8,8 @@
 //                   (same expression order as the built-in, so results can be compared)
 //   cb_rosenbrock_sharded : the same on one shard of a multi-GPU solver -- partial sums of the shard, neighbours'
 //                   boundary values from lbfgsb200_device_halo()
-//   cb_rosenbrock_syncing : cb_rosenbrock + a cudaStreamSynchronize: legal in the host-stepped loop, impossible to
-//                   capture -- the solver must fall back by itself
+//   cb_rosenbrock_syncing : cb_rosenbrock + a read-back of f to the host (copy + cudaStreamSynchronize): legal in the
+//                   host-stepped loop, impossible to capture -- the solver must fall back by itself
 //   cb_dense      : f = x^T A x + b^T x with a dense SPD A (the reference's unused fixtures,
 //                   sequential-implementation/matrices.h)
 #include <cuda_runtime.h>
@@ -134,11 +134,14 @@ int cb_rosenbrock_sharded(const double *x, const double *d, const double *d_alph
 int cb_rosenbrock_syncing(const double *x, const double *d, const double *d_alpha, double *g_out, double *d_out3, size_t n,
                           size_t global_offset, void *user, void *stream)
 {
-    const int rc = cb_rosenbrock(x, d, d_alpha, g_out, d_out3, n, global_offset, user, stream);
-    // (during a capture this fails and invalidates the capture; the return value is deliberately ignored, as a
-    // careless user would)
-    cudaStreamSynchronize((cudaStream_t)stream);
-    return rc;
+    // a callback that looks at its result on the host (logging, say): fine in the host-stepped loop, impossible to
+    // record -- the synchronisation fails while the stream is being captured and the callback reports it
+    if (cb_rosenbrock(x, d, d_alpha, g_out, d_out3, n, global_offset, user, stream)) return 1;
+    double f_host = 0.0;
+    cudaError_t e = cudaMemcpyAsync(&f_host, d_out3, sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaGetLastError();
+    return e == cudaSuccess && f_host == f_host ? 0 : 1;
 }
 
 int cb_dense(const double *x, const double *d, const double *d_alpha, double *g_out, double *d_out3, size_t n,
