@@ -166,7 +166,6 @@ k_gram(const DevState *__restrict__ st, int T, int NS, int G)
 // read back with 128-bit loads, and the consumer warps are split into NG column groups x 16/NG
 // element groups so that each row value is re-read NG times.
 constexpr int kMaxStages = 8;  // upper bound of the shared-memory ring depth (the kernels take the actual count NS <= kMaxStages)
-constexpr int kRegRecursionH = 13; // histories up to this size run the coefficient recursion out of registers (J <= 27 lanes)
 constexpr int kGramStages = 4; // ring depth of the stand-alone pass A
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -438,7 +437,9 @@ __device__ void compact_recursion(DevState *st, const double *rows, double *Gs, 
     // matrix through its 32-bit shared address computed once and made opaque to the compiler.  (Measured with the
     // diagnostic marks of benchmarks/timeline.py: with generic accesses to the dynamic array -- each re-deriving the
     // shared window from a special register -- and indexed shuffles, a step cost ~1750 cycles; a dependent
-    // LDS + DMUL + LDS + DFMA + STS chain is ~150.)
+    // LDS + DMUL + LDS + DFMA + STS chain is ~150.  A variant that kept u, rho and the lane's Gram row in REGISTERS
+    // and broadcast with shuffles -- fewer instructions on paper -- measured 18 us for the two loops against 6 us here
+    // and was dropped.)
     __shared__ double us[kMaxCols], rhos[kMaxCompactM], als[kMaxCompactM];
     unsigned gs_addr = smem_u32(Gs);
     asm volatile("mov.u32 %0, %0;" : "+r"(gs_addr)); // keep it in a register: no rematerialisation inside the loops
@@ -449,100 +450,48 @@ __device__ void compact_recursion(DevState *st, const double *rows, double *Gs, 
     };
     int bad = 0;
     double gamma;
-    if (h <= kRegRecursionH) {
-        // J <= 32: lane i keeps u_i and ITS row of the window Gram matrix (the 2h entries the steps will multiply with,
-        // loaded before the first step) in registers; a step is two shuffles, a multiply and an fma -- nothing but
-        // registers on the 2h-step dependent chain.  Same operations, same order, same bits as the general path below.
-        const bool own = lane < J;
-        double u = own ? gs_at(lane * J + jg) : 0.0; // q = g: u_i = b_i . g
-        double gy[kRegRecursionH], gsx[kRegRecursionH];
-#pragma unroll
-        for (int p = 0; p < kRegRecursionH; ++p) {
-            gy[p] = (own && p < h) ? gs_at(lane * J + h + p) : 0.0; // G[i][y_p]
-            gsx[p] = (own && p < h) ? gs_at(lane * J + p) : 0.0;    // G[i][s_p]
-        }
-        double rho = 0.0; // lane p: rho_p = 1 / (y_p . s_p)
-        if (lane < h) {
-            rho = 1.0 / gs_at((h + lane) * J + lane);
-            if (seq && !isfinite(rho)) bad = 1;
-            if (st->skip[slot_of(*st, lane)]) rho = 0.0;
-        }
-        bad = __any_sync(0xffffffffu, bad);
-        double al = 0.0, ds = 0.0; // lane p: alpha_p, then the coefficient of s_p
-#pragma unroll
-        for (int p = kRegRecursionH - 1; p >= 0; --p) { // first loop, newest -> oldest (seq/lbfgs.cpp:100-114)
-            if (p < h) {
-                const double a = __shfl_sync(0xffffffffu, rho, p) * __shfl_sync(0xffffffffu, u, p); // rho_p (s_p . q)
-                if (lane == p) al = a;
-                u = fma(-a, gy[p], u); // q -= a y_p
-            }
-        }
-        const double ys = gs_at(js * J + jy), yy = gs_at(jy * J + jy);
-        gamma = ys / yy; // :117
-        if (seq) {
-            if (gamma <= 0 || !isfinite(gamma)) bad = 1;
-        } else {
-            gamma = (yy > 0 && ys > 1e-10) ? ys / yy : 1.0; // par/L-BFGS.cu:246-255
-        }
-        u = u * gamma; // r = gamma q
-#pragma unroll
-        for (int p = 0; p < kRegRecursionH; ++p) { // second loop, oldest -> newest (:133-141)
-            if (p < h) {
-                const double beta = __shfl_sync(0xffffffffu, rho, p) * __shfl_sync(0xffffffffu, u, h + p); // rho_p (y_p . r)
-                const double c = __shfl_sync(0xffffffffu, al, p) - beta;
-                if (lane == p) ds = c;
-                u = fma(c, gsx[p], u); // r += (alpha_p - beta) s_p
-            }
-        }
-        const double al_y = __shfl_sync(0xffffffffu, al, lane >= h ? lane - h : 0);
-        if (lane < h) { delta_s[lane] = ds; als[lane] = al; }
-        else if (lane < 2 * h) delta_s[lane] = (0.0 - al_y) * gamma; // coefficient of y_p: (0 - alpha_p) gamma
-        else if (lane == jg) delta_s[jg] = 1.0 * gamma;              // coefficient of g
-        __syncwarp();
-    } else {
-        for (int i = lane; i < J; i += 32) us[i] = gs_at(i * J + jg); // q = g: u_i = b_i . g
-        // rho_p = 1 / (y_p . s_p), once per pair (seq/lbfgs.cpp:102, :135); pairs the CUDA profile skips get rho = 0, which
-        // zeroes their alpha and their (alpha - beta) exactly as the skip flag does (par/L-BFGS.cu:222-223)
-        for (int p = lane; p < h; p += 32) {
-            double rho = 1.0 / gs_at((h + p) * J + p);
-            if (seq && !isfinite(rho)) bad = 1;
-            if (st->skip[slot_of(*st, p)]) rho = 0.0;
-            rhos[p] = rho;
-        }
-        bad = __any_sync(0xffffffffu, bad);
-        __syncwarp();
-        // Every coefficient is touched exactly once (delta_{y_p} = -alpha_p in loop 1, delta_{s_p} = alpha_p - beta_p in
-        // loop 2, delta_g = 1), so the coefficients are assembled after the loops; a step only moves the projections.
-        auto bump = [&](int k, double c) { // q += c b_k : u_i += c G[i][k], every lane its own indices
-            for (int i = lane; i < J; i += 32) us[i] = fma(c, gs_at(i * J + k), us[i]);
-            __syncwarp();
-        };
-        // first loop, newest -> oldest (seq/lbfgs.cpp:100-114)
-        for (int p = h - 1; p >= 0; --p) {
-            const double a = rhos[p] * us[p];       // rho_p (s_p . q)
-            if (lane == 0) als[p] = a;
-            bump(h + p, -a);                        // q -= a y_p
-        }
-        const double ys = gs_at(js * J + jy), yy = gs_at(jy * J + jy);
-        gamma = ys / yy; // :117
-        if (seq) {
-            if (gamma <= 0 || !isfinite(gamma)) bad = 1;
-        } else {
-            gamma = (yy > 0 && ys > 1e-10) ? ys / yy : 1.0; // par/L-BFGS.cu:246-255
-        }
-        for (int i = lane; i < J; i += 32) us[i] = us[i] * gamma; // r = gamma q
-        __syncwarp();
-        // second loop, oldest -> newest (:133-141)
-        for (int p = 0; p < h; ++p) {
-            const double beta = rhos[p] * us[h + p]; // rho_p (y_p . r)
-            const double c = als[p] - beta;          // (a skipped pair has alpha = beta = 0)
-            if (lane == 0) delta_s[p] = c;           // coefficient of s_p: 0 * gamma + c
-            bump(p, c);                              // r += (alpha_p - beta) s_p
-        }
-        for (int p = lane; p < h; p += 32) delta_s[h + p] = (0.0 - als[p]) * gamma; // coefficient of y_p: (0 - alpha_p) gamma
-        if (lane == 0) delta_s[jg] = 1.0 * gamma;                                   // coefficient of g
-        __syncwarp();
+    for (int i = lane; i < J; i += 32) us[i] = gs_at(i * J + jg); // q = g: u_i = b_i . g
+    // rho_p = 1 / (y_p . s_p), once per pair (seq/lbfgs.cpp:102, :135); pairs the CUDA profile skips get rho = 0, which
+    // zeroes their alpha and their (alpha - beta) exactly as the skip flag does (par/L-BFGS.cu:222-223)
+    for (int p = lane; p < h; p += 32) {
+        double rho = 1.0 / gs_at((h + p) * J + p);
+        if (seq && !isfinite(rho)) bad = 1;
+        if (st->skip[slot_of(*st, p)]) rho = 0.0;
+        rhos[p] = rho;
     }
+    bad = __any_sync(0xffffffffu, bad);
+    __syncwarp();
+    // Every coefficient is touched exactly once (delta_{y_p} = -alpha_p in loop 1, delta_{s_p} = alpha_p - beta_p in
+    // loop 2, delta_g = 1), so the coefficients are assembled after the loops; a step only moves the projections.
+    auto bump = [&](int k, double c) { // q += c b_k : u_i += c G[i][k], every lane its own indices
+        for (int i = lane; i < J; i += 32) us[i] = fma(c, gs_at(i * J + k), us[i]);
+        __syncwarp();
+    };
+    // first loop, newest -> oldest (seq/lbfgs.cpp:100-114)
+    for (int p = h - 1; p >= 0; --p) {
+        const double a = rhos[p] * us[p];       // rho_p (s_p . q)
+        if (lane == 0) als[p] = a;
+        bump(h + p, -a);                        // q -= a y_p
+    }
+    const double ys = gs_at(js * J + jy), yy = gs_at(jy * J + jy);
+    gamma = ys / yy; // :117
+    if (seq) {
+        if (gamma <= 0 || !isfinite(gamma)) bad = 1;
+    } else {
+        gamma = (yy > 0 && ys > 1e-10) ? ys / yy : 1.0; // par/L-BFGS.cu:246-255
+    }
+    for (int i = lane; i < J; i += 32) us[i] = us[i] * gamma; // r = gamma q
+    __syncwarp();
+    // second loop, oldest -> newest (:133-141)
+    for (int p = 0; p < h; ++p) {
+        const double beta = rhos[p] * us[h + p]; // rho_p (y_p . r)
+        const double c = als[p] - beta;          // (a skipped pair has alpha = beta = 0)
+        if (lane == 0) delta_s[p] = c;           // coefficient of s_p: 0 * gamma + c
+        bump(p, c);                              // r += (alpha_p - beta) s_p
+    }
+    for (int p = lane; p < h; p += 32) delta_s[h + p] = (0.0 - als[p]) * gamma; // coefficient of y_p: (0 - alpha_p) gamma
+    if (lane == 0) delta_s[jg] = 1.0 * gamma;                                   // coefficient of g
+    __syncwarp();
     tl_mark(st, 105, global_ns()); // (both loops done)
     for (int i = lane; i < J; i += 32) st->delta[i] = delta_s[i];
     for (int p = lane; p < h; p += 32) st->alpha[p] = als[p];

@@ -21,9 +21,9 @@ for stage in "$@"; do
     scale) for N in 2 4 8; do [ $N -le $(nvidia-smi -L | wc -l) ] && timeout 400 $T --nproc-per-node $N --master-port 2953$N bench.py --gpus $N --no-cpu-baseline --single-variant 2>$O/bench_n$N.err | grep '^{' > $O/bench_n$N.json; cut -c1-200 $O/bench_n$N.json; done ;;
     config4) N=$(nvidia-smi -L | wc -l); timeout 900 $T --nproc-per-node $N --master-port 29540 bench.py --gpus $N --config 4 2>$O/config4.err | grep '^{' > $O/config4_n$N.json; cut -c1-300 $O/config4_n$N.json; tail -3 $O/config4.err ;;
     config5) N=$(nvidia-smi -L | wc -l); timeout 900 $T --nproc-per-node $N --master-port 29555 bench.py --gpus $N --config 5 2>$O/config5.err | grep '^{' > $O/config5_n$N.json; cut -c1-300 $O/config5_n$N.json; tail -3 $O/config5.err ;;
-    ncu) B="python bench.py --steps 4 --warmup 12 --no-cpu-baseline --single-variant --sustain 0 --graph 0"
+    ncu) B="python bench.py --steps 12 --warmup 12 --no-cpu-baseline --single-variant --sustain 0 --graph 0"
          $B > $O/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 120 --csv --log-file $O/launches.csv $B > $O/ncu1.log 2>&1
-         ncu --set full --clock-control none --import-source on -k regex:"k_accept_gram|k_combine_trial|k_trial" -s 96 -c 6 -o $O/prof $B > $O/ncu2.log 2>&1; ls -la $O | tail -5 ;;
+         ncu --set full --clock-control none --import-source on -k regex:"k_accept_gram|k_combine_trial|k_trial" -s 60 -c 9 -o $O/prof $B > $O/ncu2.log 2>&1; ls -la $O | tail -5 ;;
     e2e) timeout 600 python benchmarks/e2e_breakdown.py 100000000 42 > $O/e2e_1e8.jsonl 2>&1; cat $O/e2e_1e8.jsonl | cut -c1-420
          timeout 600 python benchmarks/e2e_breakdown.py 12500000 42 > $O/e2e_125e5.jsonl 2>&1; cat $O/e2e_125e5.jsonl | cut -c1-420 ;;
     timeline) N=$(nvidia-smi -L | wc -l); timeout 120 python benchmarks/timeline.py --size 12500000 2>/dev/null | grep '^{' > $O/timeline.jsonl
