@@ -525,7 +525,7 @@ def run_config4(b, args):
         line = {"metric": "L-BFGS iterations/sec (FP64) at n=%.0e, m=%d" % (n_global, m), "value": run["value"], "unit": "iterations/s",
                 "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": run["ms_per_step"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "BASELINE config 4: Rosenbrock n=%d, m=%d, Wolfe, compact direction (fused flow), CUDA-graph "
+                "config": {"workload": "BASELINE config 4: Rosenbrock n=%d, m=%d, Wolfe, compact direction (m > 13: stand-alone pass A + combine kernels), CUDA-graph "
                                        "loop, contiguous shards x%d with 1-element halo + packed exchange" % (n_global, m, world),
                            "trials_per_step": run["trials_per_step"],
                            "cache": "each of the 2m+6 vectors is %.2f GB per GPU" % (8.0 * n_local / 1e9)},
@@ -562,7 +562,7 @@ def run_config5(b, args):
                           "unit": "iterations/s", "n_gpus": world, "steps": K, "warmup": 3, "ms_per_step": best["ms_per_step"],
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": {"workload": "BASELINE config 5: Rosenbrock n=%d, Wolfe, m in %s, explicit two-loop vs compact "
-                                                 "(fused flow), CUDA-graph loop, x%d GPUs; value = the m=10 compact entry" %
+                                                 "(fused flow for m <= 13), CUDA-graph loop, x%d GPUs; value = the m=10 compact entry" %
                                                  (n_global, hists, world)},
                           "peak": b.peak, "peak_source": b.peak_src, "sweep": sweep}))
     return 0

@@ -438,6 +438,41 @@ def test_unfused_and_cp_async_paths_match_oracle(gpu, oracle, monkeypatch, env):
             assert relvec(x, xo) <= TOL_ITERATE, (env, objective, graph, relvec(x, xo))
 
 
+@pytest.mark.parametrize("env", [{}, {"LBFGSB200_CT_TILE": "256,3"}, {"LBFGSB200_CT_TILE": "256,5", "LBFGSB200_AG_TILE": "256,3"},
+                                 {"LBFGSB200_AG_BOXES": "3"}, {"LBFGSB200_AG_BOXES": "0"}])
+def test_fused_flow_is_repeatable_with_odd_ring_depths(gpu, monkeypatch, env):
+    """Regression test for a phase-aliasing race of k_combine_trial: with an ODD number of ring stages its two consumer
+    groups used to alternate on a stage, and the group running ahead could pass a stage's `full` barrier one phase early
+    (mbarrier waits go by parity, TMA loads complete out of order) and consume a tile still in flight -- different bits
+    from run to run, or a trapped launch.  m = 8 and 9 get 5-stage rings by default; the environment forces 3 and 5.
+    Every run must give the same bits, the bits of the unfused flow's decisions, and the box layouts of k_accept_gram
+    (merged / separate TMA boxes) must agree bit for bit."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    n, K = 1 << 22, 12
+    x0 = gpu.x0_uniform(n, -2, 2)
+    for m in (8, 9):
+        p = gpu.default_params("par", m=m, line_search="wolfe", max_iterations=K, tolerance=0.0)
+        ref = None
+        for rep in range(3):
+            s = gpu.Solver("rosenbrock", n, p, trace_rows=K)
+            s.set_x0(x0)
+            s.iterate(K)
+            x, r, tr = s.x(), s.result(), s.trace()
+            s.destroy()
+            assert r["flow"] == 2 and r["iterations"] == K, (env, m, r)
+            if ref is None:
+                ref = (x, tr)
+            else:
+                assert np.array_equal(x, ref[0]) and np.array_equal(tr, ref[1]), (env, m, rep)
+        key = "x_m%d" % m
+        first = _REPEATABLE_BITS.setdefault(key, ref[0])  # the same bits under every environment of this test
+        assert np.array_equal(first, ref[0]), (env, m)
+
+
+_REPEATABLE_BITS = {}
+
+
 def test_pending_steepest_and_rejected_pair_paths_of_the_fused_flow(gpu, oracle):
     """Rare branches of the fused compact flow, from the seeded harsh starts of the test above (U(-4,4), tiny n) with
     small and large m: a pair rejected by the curvature gate with a FULL ring (the stand-alone pass A re-computes the
