@@ -438,40 +438,52 @@ __device__ void compact_recursion(DevState *st, const double *rows, double *Gs, 
     // diagnostic marks of benchmarks/timeline.py: with generic accesses to the dynamic array -- each re-deriving the
     // shared window from a special register -- and indexed shuffles, a step cost ~1750 cycles; a dependent
     // LDS + DMUL + LDS + DFMA + STS chain is ~150.  A variant that kept u, rho and the lane's Gram row in REGISTERS
-    // and broadcast with shuffles -- fewer instructions on paper -- measured 18 us for the two loops against 6 us here
-    // and was dropped.)
+    // and broadcast with shuffles -- 58 cycles per step in isolation (benchmarks/micro/latency.cu) -- measured 19 us for
+    // the two loops inside this kernel against 7.5 us for the loops below, with or without a convergence point in
+    // front of it, and was dropped; why this kernel runs its dependent chains ~3x slower than the micro-benchmark does
+    // is not understood.)
     __shared__ double us[kMaxCols], rhos[kMaxCompactM], als[kMaxCompactM];
-    unsigned gs_addr = smem_u32(Gs);
-    asm volatile("mov.u32 %0, %0;" : "+r"(gs_addr)); // keep it in a register: no rematerialisation inside the loops
-    auto gs_at = [&](int idx) {
+    // 32-bit shared addresses, computed once and made opaque to the compiler: left to itself it re-derives the shared
+    // window from SR_CgaCtaId (an S2R of several hundred cycles) in EVERY iteration of the loops below, for the static
+    // arrays as well as for the dynamic one
+    auto opaque = [](const void *p) {
+        unsigned a = smem_u32(p);
+        asm volatile("mov.u32 %0, %0;" : "+r"(a));
+        return a;
+    };
+    const unsigned gs_a = opaque(Gs), us_a = opaque(us), rh_a = opaque(rhos), al_a = opaque(als), ds_a = opaque(delta_s);
+    auto lds = [](unsigned a) {
         double v;
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(gs_addr + 8u * (unsigned)idx));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
         return v;
     };
+    auto sts = [](unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); };
+    auto gs_at = [&](int idx) { return lds(gs_a + 8u * (unsigned)idx); };
     int bad = 0;
     double gamma;
-    for (int i = lane; i < J; i += 32) us[i] = gs_at(i * J + jg); // q = g: u_i = b_i . g
+    __syncwarp(); // (converged from here on: thread 0 has just been off on its own in tl_mark)
+    for (int i = lane; i < J; i += 32) sts(us_a + 8u * i, gs_at(i * J + jg)); // q = g: u_i = b_i . g
     // rho_p = 1 / (y_p . s_p), once per pair (seq/lbfgs.cpp:102, :135); pairs the CUDA profile skips get rho = 0, which
     // zeroes their alpha and their (alpha - beta) exactly as the skip flag does (par/L-BFGS.cu:222-223)
     for (int p = lane; p < h; p += 32) {
         double rho = 1.0 / gs_at((h + p) * J + p);
         if (seq && !isfinite(rho)) bad = 1;
         if (st->skip[slot_of(*st, p)]) rho = 0.0;
-        rhos[p] = rho;
+        sts(rh_a + 8u * p, rho);
     }
     bad = __any_sync(0xffffffffu, bad);
     __syncwarp();
     // Every coefficient is touched exactly once (delta_{y_p} = -alpha_p in loop 1, delta_{s_p} = alpha_p - beta_p in
     // loop 2, delta_g = 1), so the coefficients are assembled after the loops; a step only moves the projections.
     auto bump = [&](int k, double c) { // q += c b_k : u_i += c G[i][k], every lane its own indices
-        for (int i = lane; i < J; i += 32) us[i] = fma(c, gs_at(i * J + k), us[i]);
+        for (int i = lane; i < J; i += 32) sts(us_a + 8u * i, fma(c, gs_at(i * J + k), lds(us_a + 8u * i)));
         __syncwarp();
     };
     // first loop, newest -> oldest (seq/lbfgs.cpp:100-114)
     for (int p = h - 1; p >= 0; --p) {
-        const double a = rhos[p] * us[p];       // rho_p (s_p . q)
-        if (lane == 0) als[p] = a;
-        bump(h + p, -a);                        // q -= a y_p
+        const double a = lds(rh_a + 8u * p) * lds(us_a + 8u * p); // rho_p (s_p . q)
+        if (lane == 0) sts(al_a + 8u * p, a);
+        bump(h + p, -a);                                          // q -= a y_p
     }
     const double ys = gs_at(js * J + jy), yy = gs_at(jy * J + jy);
     gamma = ys / yy; // :117
@@ -480,17 +492,17 @@ __device__ void compact_recursion(DevState *st, const double *rows, double *Gs, 
     } else {
         gamma = (yy > 0 && ys > 1e-10) ? ys / yy : 1.0; // par/L-BFGS.cu:246-255
     }
-    for (int i = lane; i < J; i += 32) us[i] = us[i] * gamma; // r = gamma q
+    for (int i = lane; i < J; i += 32) sts(us_a + 8u * i, lds(us_a + 8u * i) * gamma); // r = gamma q
     __syncwarp();
     // second loop, oldest -> newest (:133-141)
     for (int p = 0; p < h; ++p) {
-        const double beta = rhos[p] * us[h + p]; // rho_p (y_p . r)
-        const double c = als[p] - beta;          // (a skipped pair has alpha = beta = 0)
-        if (lane == 0) delta_s[p] = c;           // coefficient of s_p: 0 * gamma + c
-        bump(p, c);                              // r += (alpha_p - beta) s_p
+        const double beta = lds(rh_a + 8u * p) * lds(us_a + 8u * (h + p)); // rho_p (y_p . r)
+        const double c = lds(al_a + 8u * p) - beta;                        // (a skipped pair has alpha = beta = 0)
+        if (lane == 0) sts(ds_a + 8u * p, c);                              // coefficient of s_p: 0 * gamma + c
+        bump(p, c);                                                        // r += (alpha_p - beta) s_p
     }
-    for (int p = lane; p < h; p += 32) delta_s[h + p] = (0.0 - als[p]) * gamma; // coefficient of y_p: (0 - alpha_p) gamma
-    if (lane == 0) delta_s[jg] = 1.0 * gamma;                                   // coefficient of g
+    for (int p = lane; p < h; p += 32) sts(ds_a + 8u * (h + p), (0.0 - lds(al_a + 8u * p)) * gamma); // coefficient of y_p: (0 - alpha_p) gamma
+    if (lane == 0) sts(ds_a + 8u * jg, 1.0 * gamma);                                                 // coefficient of g
     __syncwarp();
     tl_mark(st, 105, global_ns()); // (both loops done)
     for (int i = lane; i < J; i += 32) st->delta[i] = delta_s[i];
