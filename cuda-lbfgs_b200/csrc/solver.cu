@@ -179,7 +179,7 @@ struct lbfgsb200_solver {
     bool cb_graph_failed = false;            // the callback could not be stream-captured: host-stepped loop instead
     accept_kernel_t accept_kernel = nullptr;
 
-    double *arena = nullptr;    // x, x_alt, g, w, S[nslots], Y[nslots]
+    double *arena = nullptr;    // rows x_a, g, w, x_b, S[nslots], Y[nslots] (compact.cuh: kArenaRow*)
     double *partials = nullptr; // [kMaxQ][grid]
     double *pkt = nullptr;      // send [kPacket] + recv [nranks][kPacket]
     double *trace = nullptr;

@@ -72,7 +72,7 @@ struct DevState {
     int rank, nranks;
     int grid;         // CTAs of the 4-per-SM streaming kernels (partial count is passed per launch)
     int grid_accept;  // CTAs of the accept kernel
-    double *arena0;            // row 0 of the arena (tensor-map row arithmetic: x is row 0 or 1)
+    double *arena0;            // row 0 of the arena = x_a (tensor-map row arithmetic: x is row 0 or row 3)
     double *x, *x_alt, *g, *w; // w: two-loop work vector q/r, ends as the direction d;
                                // x_alt: the accept kernel writes the new iterate here, then x <-> x_alt
     double *S, *Y;     // ring buffers, nslots rows of `stride` doubles
