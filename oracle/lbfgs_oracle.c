@@ -5,7 +5,7 @@
  * reference's operation order kept expression by expression so that, built
  * without FMA contraction (-ffp-contract=off), every intermediate is
  * bit-identical to the unmodified reference compiled for x86-64
- * (oracle/_ref/, checked by tests/test_oracle_vs_ref.py and the golden traces).
+ * (oracle/_ref/, checked by tests/test_oracle.py and the golden traces).
  *
  * seq/ = /root/reference/sequential-implementation/
  * par/ = /root/reference/parallel-implementation/
