@@ -218,8 +218,10 @@ def run_reference_arm(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "Rosenbrock n=1e8, m=10, Wolfe line search (hybrid CPU reference: sequential-implementation/"
                                    "lbfgs.cpp + parallel-implementation/line_search.cpp, unmodified, 1 core); each step is "
-                                   "measured on a bounded sample: n=1e7 (10 %% of the workload) with a full history, "
-                                   "%.2f s per iteration measured, value = that rate / 10" % cb["seconds_per_iteration_at_sample"],
+                                   "measured on a bounded sample: n=%d (1/%d of the workload) with a full history, "
+                                   "%.2f s per iteration measured, value = that rate x %d / %d" %
+                                   (REF_ARM_SAMPLE_N, N_GLOBAL // REF_ARM_SAMPLE_N, cb["seconds_per_iteration_at_sample"],
+                                    REF_ARM_SAMPLE_N, N_GLOBAL),
                        "sample_n": REF_ARM_SAMPLE_N, "same_config": False},
             "cpu_baseline": cb, "config1": config1,
             "e2e": {"value": cb["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
