@@ -40,11 +40,14 @@ def main():
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--direction", default="compact")
+    ap.add_argument("--sub", type=int, default=0, help="1: also record the sub-marks inside OP_F_ACCEPT (they cost ~1 us each)")
     ap.add_argument("--heat-ms", type=float, default=1500.0,
                     help="iterate this long before the measured window: a GPU that has been idle runs its SMs at ~1 GHz for "
                          "the first tens of milliseconds, which inflates the scalar kernels (not the HBM-bound vector kernels)")
     args = ap.parse_args()
     os.environ["LBFGSB200_TIMELINE"] = str(64 * (args.iters + args.hist + 8))
+    if args.sub:
+        os.environ["LBFGSB200_TIMELINE_SUB"] = "1"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     pkg = load_pkg()

@@ -380,7 +380,7 @@ __device__ __forceinline__ unsigned long long global_ns()
 }
 __device__ __forceinline__ void tl_mark(DevState *st, int op, unsigned long long t_in)
 {
-    if (st->tl && threadIdx.x == 0 && st->tl_n < st->tl_cap) {
+    if (st->tl && threadIdx.x == 0 && st->tl_n < st->tl_cap && (op < 100 || st->tl_sub)) {
         unsigned long long *row = st->tl + 3 * (size_t)st->tl_n++;
         row[0] = (unsigned long long)(long long)op;
         row[1] = t_in;

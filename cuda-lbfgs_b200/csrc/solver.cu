@@ -1300,6 +1300,7 @@ int lbfgsb200_create(lbfgsb200_solver_t **out, int objective, size_t n_global,
     st.lsp.wolfe_min = params->wolfe_min;
     st.status = LBFGSB200_RUNNING;
     st.tl_cap = tl_cap;
+    st.tl_sub = getenv("LBFGSB200_TIMELINE_SUB") ? 1 : 0;
     st.tl = s->timeline;
     if (s->arena_maps) {
         CREATE_RC(build_arena_maps(s, s->arena_maps, s->gram_T, 0));
@@ -1482,7 +1483,7 @@ int lbfgsb200_checkpoint_load(lbfgsb200_solver_t *s, const char *path)
     st.gram = cur.gram; st.gram_rows = cur.gram_rows; st.gram_recv = cur.gram_recv; st.delta = cur.delta;
     st.mail = cur.mail; st.peers = cur.peers; st.p2p = cur.p2p; st.p2p_timeout_ns = cur.p2p_timeout_ns;
     st.cond_outer = cur.cond_outer; st.cond_inner = cur.cond_inner; st.cond_fix = cur.cond_fix; st.use_graph = cur.use_graph;
-    st.tl = cur.tl; st.tl_cap = cur.tl_cap; st.tl_n = cur.tl_n;
+    st.tl = cur.tl; st.tl_cap = cur.tl_cap; st.tl_n = cur.tl_n; st.tl_sub = cur.tl_sub;
     st.max_iterations = cur.max_iterations; st.tolerance = cur.tolerance; st.lsp = cur.lsp; // the new handle's limits apply
     if (st.status != LBFGSB200_CONVERGED && st.status != LBFGSB200_LS_FAILED && st.k < st.max_iterations) {
         st.status = LBFGSB200_RUNNING; // a run that only ran out of iterations may continue

@@ -135,7 +135,7 @@ struct DevState {
     // ---- fused compact flow ----
     int fused;          // 1: k_accept_gram / k_combine_trial flow
     int pend_steepest;  // the descent safeguard fired AFTER the combine pass: the next k_trial rewrites d = -g itself
-    int pad0;
+    int tl_sub;         // diagnostic timeline: also record the sub-marks inside OP_F_ACCEPT (each costs ~1 us: LBFGSB200_TIMELINE_SUB)
     long long iters_left; // iteration budget of the current iterate() call
 
     // ---- accounting: algorithmic HBM traffic in units of one local vector (8 n bytes) ----
